@@ -1,0 +1,152 @@
+/*
+ * tz_abi.h -- C-ABI of libtz_b200.so: the batched MCTS hot path of lowrollr/turbozero as
+ * hand-written sm_100a CUDA kernels.
+ *
+ * The reference has no FFI: its search is Python/JAX traced into XLA.  Each entry point below
+ * replaces the XLA computation that one reference method lowers to; the reference location is
+ * cited on every declaration (paths relative to the reference repo root).  A jax.ffi / ctypes /
+ * cffi binding passes raw device pointers and a stream; no framework types cross this boundary.
+ *
+ * Conventions
+ *  - All array arguments are DEVICE pointers unless the name ends in `_host`.
+ *  - Layout is the reference's batched pytree layout (core/evaluators/evaluator.py:42-45 adds
+ *    the leading batch axis to core/trees/tree.py:11-19): batch-major, struct-of-arrays,
+ *    row-major, dense.  bool is one byte (0/1).
+ *  - Every call is asynchronous on `stream`, never allocates, never synchronises, never throws.
+ *    Return value: TZ_OK (0), a negative TZ_E* code, or a positive cudaError_t from the launch.
+ *  - The tree arrays are updated IN PLACE (the reference returns new pytrees; XLA aliases them).
+ *  - Invariant kept by every entry point (and by the reference): rows >= next_free_idx are null
+ *    (-1 in parents/edge_map, zero bytes in every data leaf).
+ *  - Thread-safety: re-entrant; calls on the same tree must be stream-ordered by the caller.
+ */
+#ifndef TZ_ABI_H_
+#define TZ_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TZ_ABI_VERSION 1
+#define TZ_MAX_EMB 24 /* max number of embedding pytree leaves per node */
+#define TZ_PATH_CAP 32 /* path slots kept per tree between select and backprop */
+
+#define TZ_OK 0
+#define TZ_EINVAL (-1)   /* bad argument (null pointer, B/N/F <= 0, unknown selector, ...) */
+#define TZ_ENOTSUP (-2)  /* configuration outside what the kernels implement */
+
+#define TZ_NULL_INDEX (-1) /* core/trees/tree.py:21 */
+#define TZ_ROOT_INDEX 0    /* core/trees/tree.py:23 */
+
+typedef void* tz_stream_t; /* cudaStream_t */
+
+/* One batch of B fixed-capacity trees: core/trees/tree.py:11-19 (Tree) holding
+ * core/evaluators/mcts/state.py:12-25 (MCTSNode) or weighted_mcts.py:14-17 (WeightedMCTSNode). */
+typedef struct TzTree {
+  int32_t B;                /* trees in this batch (envs on this device) */
+  int32_t N;                /* max_nodes  (mcts.py:22) */
+  int32_t F;                /* branching_factor (mcts.py:21) */
+  int32_t n_emb;            /* number of embedding leaves, 0..TZ_MAX_EMB */
+  int32_t* next_free_idx;   /* [B]      tree.py:15 */
+  int32_t* parents;         /* [B,N]    tree.py:16 */
+  int32_t* edge_map;        /* [B,N,F]  tree.py:17 */
+  int32_t* n;               /* [B,N]    state.py:21 visit count */
+  float* p;                 /* [B,N,F]  state.py:22 policy */
+  float* q;                 /* [B,N]    state.py:23 value estimate */
+  float* r;                 /* [B,N] raw leaf value, weighted_mcts.py:17; NULL for plain MCTS */
+  uint8_t* terminated;      /* [B,N]    state.py:24 */
+  void* emb[TZ_MAX_EMB];    /* [B,N,emb_row_bytes[k]]  state.py:25, one table per pytree leaf */
+  int64_t emb_row_bytes[TZ_MAX_EMB];
+  uint64_t* stats;          /* optional [B,4] counters {select levels, simulations, rows before
+                               re-root, rows kept by re-root}; NULL disables counting */
+} TzTree;
+
+/* Action selectors: core/evaluators/mcts/action_selection.py */
+#define TZ_SEL_PUCT 0        /* PUCTSelector :61-116 */
+#define TZ_SEL_MUZERO_PUCT 1 /* MuZeroPUCTSelector :119-177 (intended maths) */
+
+typedef struct TzSearchCfg {
+  int32_t selector;      /* TZ_SEL_* */
+  float c;               /* PUCTSelector.c  (action_selection.py:67) */
+  float c1, c2;          /* MuZeroPUCTSelector (action_selection.py:123-124) */
+  float epsilon;         /* selector epsilon (action_selection.py:41,68) */
+  float discount;        /* MCTS.discount (mcts.py:24) */
+  int32_t weighted;      /* 0: MCTS.backpropagate mcts.py:231-262; 1: WeightedMCTS weighted_mcts.py:90-152 */
+  float inv_q_temperature; /* float32(1/q_temperature) if q_temperature > 0, else 0 (weighted_mcts.py:113-131) */
+  int32_t fma_backup;    /* 1: q update as fmaf(q, n, v) / (n+1) (XLA may contract mcts.py:322); 0: separate mul, add */
+} TzSearchCfg;
+
+/* Per-simulation exchange buffers between the kernels and the host framework's
+ * env_step_fn / eval_fn (mcts.py:160-172).  Caller-allocated. */
+typedef struct TzWork {
+  int32_t* parent;          /* [B]  out of select: TraversalState.parent (state.py:43) */
+  int32_t* action;          /* [B]  out of select: TraversalState.action (state.py:44) */
+  void* emb_parent[TZ_MAX_EMB]; /* [B,row_k] out of select: tree.data_at(parent).embedding (mcts.py:164) */
+  float* policy;            /* [B,F] in to expand: masked+softmaxed policy (mcts.py:170-171) */
+  float* value;             /* [B]   in: where(terminated, player_reward, value) (mcts.py:172) */
+  uint8_t* terminated;      /* [B]   in: metadata.terminated (mcts.py:172,179-180) */
+  void* emb_new[TZ_MAX_EMB];/* [B,row_k] in: new_embedding (mcts.py:165) */
+  float* backprop_noise;    /* [B,F] in, weighted q_temperature==0 only: uniform(0,tiebreak_noise) (weighted_mcts.py:123); else NULL */
+  int32_t* path;            /* [B,TZ_PATH_CAP+1] scratch owned by the library between select and the
+                               following expand_backprop of the same trees; NULL = walk parents[] */
+} TzWork;
+
+int tz_abi_version(void);
+const char* tz_strerror(int code);
+
+/* Tree.reset / init_tree over the whole allocation: core/trees/tree.py:272-298. Writes every row. */
+int tz_tree_init(const TzTree* t, tz_stream_t stream);
+
+/* MCTS.update_root_node + Tree.set_root: mcts.py:363-384 (weighted_mcts.py:66-87), tree.py:135-150.
+ * root_policy [B,F], root_value [B], root_emb[k] [B,row_k]. */
+int tz_set_root(const TzTree* t, const float* root_policy, const float* root_value,
+                void* const* root_emb, tz_stream_t stream);
+
+/* MCTS.traverse with the selector inlined: mcts.py:192-228, action_selection.py:91-116, tree.py:78-98.
+ * Fills w->parent, w->action, w->emb_parent (mcts.py:161-164) and w->path. */
+int tz_select(const TzTree* t, const TzSearchCfg* cfg, const TzWork* w, tz_stream_t stream);
+
+/* Second half of MCTS.iterate: node_exists test, visit_node/new_node, update_node/add_node and
+ * backpropagate: mcts.py:174-189, 231-262, 299-360; tree.py:101-132,153-166; weighted_mcts.py:43-63,90-152. */
+int tz_expand_backprop(const TzTree* t, const TzSearchCfg* cfg, const TzWork* w, tz_stream_t stream);
+
+/* tz_expand_backprop for simulation i followed by tz_select for simulation i+1 in ONE launch. */
+int tz_expand_backprop_select(const TzTree* t, const TzSearchCfg* cfg, const TzWork* w,
+                              tz_stream_t stream);
+
+/* MCTS.sample_root_action + MCTS.get_value: mcts.py:265-296, 111-120.
+ * visits [B,F] int32 (may be NULL), policy_weights [B,F] (may be NULL), root_q [B] (may be NULL),
+ * action [B] (may be NULL).  temperature == 0: argmax(policy_weights + noise[B,F]) with noise =
+ * uniform(0, tiebreak_noise) supplied by the caller (mcts.py:281-285).  temperature > 0:
+ * jax.random.choice(p = pw**(1/T) renormalised) driven by uniform01[B] (mcts.py:288-294). */
+int tz_root_action(const TzTree* t, float temperature, const float* noise, const float* uniform01,
+                   int32_t* visits, float* policy_weights, float* root_q, int32_t* action,
+                   tz_stream_t stream);
+
+/* MCTS.step / MCTS.reset fused with the caller's select (core/common.py:89-94):
+ * per tree, reset_flag[b] != 0 (or persist_tree == 0) -> Tree.reset (tree.py:272-278);
+ * else Tree.get_subtree(action[b]) (tree.py:169-269).  reset_flag may be NULL (no resets);
+ * action may be NULL only if persist_tree == 0 or every tree is reset.
+ * Needs N*4 + <=64 KB of shared memory per CTA: N <= ~40000. */
+int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag, int persist_tree,
+              tz_stream_t stream);
+
+/* Callback that enqueues the host framework's env_step_fn + eval_fn + mask/softmax (mcts.py:160-172)
+ * on `stream` for simulation `sim`, reading w->parent/action/emb_parent and filling
+ * w->policy/value/terminated/emb_new.  Must not synchronise.  Non-zero return aborts the search. */
+typedef int (*tz_leaf_fn)(void* user, int sim, const TzWork* w, tz_stream_t stream);
+
+/* The lax.scan of MCTS.evaluate (mcts.py:99-100): num_iterations x iterate, as
+ * select, then per simulation { leaf(user), expand_backprop[_select] }.  Enqueues only. */
+int tz_search(const TzTree* t, const TzSearchCfg* cfg, const TzWork* w, int num_iterations,
+              tz_leaf_fn leaf, void* user, tz_stream_t stream);
+
+/* Number of kernels this library has launched since load (for bench accounting). */
+uint64_t tz_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TZ_ABI_H_ */

@@ -1,0 +1,209 @@
+"""Shared drivers for the parity tests: the same self-play schedule run through
+ (a) the literal NumPy restatement (oracle/mcts_numpy.py, per tree),
+ (b) the C oracle step by step in the device's batched call order (oracle/tz_oracle.c via oracle/c_oracle.py),
+ (c) the C oracle tree-major (tzo_selfplay), and -- in the gpu tests -- (d) the CUDA path through the C-ABI.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import List, Optional
+
+import numpy as np
+
+from oracle import c_oracle as CO
+from oracle import mcts_numpy as M
+from oracle import synth_numpy as SN
+
+
+@dataclass
+class Schedule:
+    """Everything random is drawn up front so every implementation consumes identical inputs."""
+    game: SN.SynthGame
+    B: int
+    N: int
+    S: int
+    moves: int
+    temperature: float = 1.0
+    persist_tree: bool = True
+    dirichlet: bool = True
+    dir_eps: float = 0.25
+    dir_alpha: float = 0.3
+    weighted: bool = False
+    q_temperature: float = 1.0
+    selector: int = 0
+    discount: float = -1.0
+    c: float = 1.0
+    fma_backup: bool = False
+    tiebreak_noise: float = 1e-8
+    seed: int = 0
+    env_offset: int = 0
+
+    def __post_init__(self):
+        rng = np.random.default_rng(self.seed + 7919 * self.env_offset)
+        B, F, mv = self.B, self.game.F, self.moves
+        self.dir_noise = (rng.dirichlet([self.dir_alpha] * F, size=(mv, B)).astype(np.float32)
+                          if self.dirichlet else None)
+        self.root_noise = (rng.random((mv, B, F), dtype=np.float32) * np.float32(self.tiebreak_noise)).astype(np.float32)
+        self.uniform01 = rng.random((mv, B), dtype=np.float32)
+        self.bp_noise = ((rng.random((mv, self.S, B, F), dtype=np.float32) * np.float32(self.tiebreak_noise)).astype(np.float32)
+                         if (self.weighted and self.q_temperature == 0) else None)
+
+    def np_cfg(self) -> M.SearchCfg:
+        return M.SearchCfg(selector=self.selector, c=self.c, discount=self.discount, weighted=self.weighted,
+                           q_temperature=self.q_temperature, fma_backup=self.fma_backup)
+
+    def c_cfg(self):
+        return CO.make_cfg(selector=self.selector, c=self.c, discount=self.discount, weighted=self.weighted,
+                           q_temperature=self.q_temperature, fma_backup=self.fma_backup)
+
+    def c_game(self):
+        g = self.game
+        return CO.make_game(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
+
+
+@dataclass
+class Result:
+    arrays: dict  # final tree arrays, batched
+    actions: np.ndarray  # [moves,B]
+    pw: np.ndarray  # [moves,B,F]
+    snapshots: Optional[List[dict]] = None  # per move, after search (before re-root)
+
+
+def run_numpy(s: Schedule, snapshots: bool = False) -> Result:
+    g, cfg = s.game, s.np_cfg()
+    rbs = g.emb_row_bytes
+    trees = [M.init_tree(s.N, g.F, rbs, weighted=s.weighted) for _ in range(s.B)]
+    actions = np.zeros((s.moves, s.B), np.int32)
+    pw = np.zeros((s.moves, s.B, g.F), np.float32)
+    snaps = [] if snapshots else None
+    for b in range(s.B):
+        env_id = b + s.env_offset
+        episode = 0
+        emb = g.init_state(env_id, episode)
+        for m in range(s.moves):
+            a, w, _ = SN.evaluate(
+                trees[b], g, cfg, emb, s.S, s.temperature,
+                dir_noise=None if s.dir_noise is None else s.dir_noise[m, b], dir_eps=s.dir_eps,
+                root_noise=s.root_noise[m, b], uniform01=s.uniform01[m, b],
+                bp_noise=None if s.bp_noise is None else s.bp_noise[m, :, b])
+            actions[m, b], pw[m, b] = a, w
+            if snapshots:
+                if b == 0:
+                    snaps.append([])
+                snaps[m].append(trees[b].copy())
+            emb, episode, rf = SN.env_step(g, env_id, episode, emb, a)
+            if rf:
+                M.reset(trees[b])
+            else:
+                M.step(trees[b], a, s.persist_tree)
+    res = Result(stack_trees(trees), actions, pw)
+    if snapshots:
+        res.snapshots = [stack_trees(ts) for ts in snaps]
+    return res
+
+
+def stack_trees(trees: List[M.Tree]) -> dict:
+    d = {
+        "next_free_idx": np.array([t.next_free_idx for t in trees], np.int32),
+        "parents": np.stack([t.parents for t in trees]),
+        "edge_map": np.stack([t.edge_map for t in trees]),
+        "n": np.stack([t.n for t in trees]),
+        "p": np.stack([t.p for t in trees]),
+        "q": np.stack([t.q for t in trees]),
+        "terminated": np.stack([t.terminated for t in trees]),
+    }
+    if trees[0].r is not None:
+        d["r"] = np.stack([t.r for t in trees])
+    for k in range(len(trees[0].emb)):
+        d[f"emb{k}"] = np.stack([t.emb[k] for t in trees])
+    return d
+
+
+def run_c_stepwise(s: Schedule, snapshots: bool = False) -> Result:
+    """The C oracle driven in the batched launch order the device uses."""
+    g, cg, cfg = s.game, s.c_game(), s.c_cfg()
+    B, F, P = s.B, g.F, g.payload_bytes
+    rbs = g.emb_row_bytes
+    t = CO.HostTrees(B, s.N, F, rbs, weighted=s.weighted)
+    w = CO.HostWork(B, F, rbs, with_noise=s.bp_noise is not None)
+    episode = np.zeros((B,), np.int32)
+    core = np.zeros((B, 4), np.int32)
+    payload = np.zeros((B, P), np.uint8) if P > 0 else None
+    CO.synth_init_states(cg, B, s.env_offset, episode, core, payload)
+    rp = np.zeros((B, F), np.float32)
+    rv = np.zeros((B,), np.float32)
+    reset_flag = np.zeros((B,), np.uint8)
+    actions = np.zeros((s.moves, B), np.int32)
+    pw = np.zeros((s.moves, B, F), np.float32)
+    snaps = [] if snapshots else None
+    for m in range(s.moves):
+        CO.synth_root(cg, B, core, None if s.dir_noise is None else np.ascontiguousarray(s.dir_noise[m]), s.dir_eps, rp, rv)
+        CO.set_root(t, rp, rv, [core.view(np.uint8).reshape(B, 16)] + ([payload] if P > 0 else []))
+        for it in range(s.S):
+            CO.select(t, cfg, w)
+            CO.synth_leaf(cg, B, w.emb_parent[0].view(np.int32).reshape(B, 4), w.action, w.policy, w.value, w.terminated,
+                          w.emb_new[0].view(np.int32).reshape(B, 4), w.emb_new[1] if P > 0 else None)
+            if s.bp_noise is not None:
+                w.backprop_noise[:] = s.bp_noise[m, it]
+            CO.expand_backprop(t, cfg, w)
+        act, pwm, _, _ = CO.root_action(t, s.temperature, np.ascontiguousarray(s.root_noise[m]),
+                                        np.ascontiguousarray(s.uniform01[m]))
+        actions[m], pw[m] = act, pwm
+        if snapshots:
+            snaps.append({k: v.copy() for k, v in t.arrays().items()})
+        CO.synth_env_step(cg, B, s.env_offset, act, core, payload, episode, reset_flag)
+        CO.reroot(t, act, reset_flag, s.persist_tree)
+    res = Result({k: v.copy() for k, v in t.arrays().items()}, actions, pw, snaps)
+    res.stats = t.stats.copy()
+    return res
+
+
+def run_c_treemajor(s: Schedule, nthreads: int = 0) -> Result:
+    g, cg, cfg = s.game, s.c_game(), s.c_cfg()
+    B, F, P = s.B, g.F, g.payload_bytes
+    t = CO.HostTrees(B, s.N, F, g.emb_row_bytes, weighted=s.weighted)
+    episode = np.zeros((B,), np.int32)
+    core = np.zeros((B, 4), np.int32)
+    payload = np.zeros((B, P), np.uint8) if P > 0 else None
+    CO.synth_init_states(cg, B, s.env_offset, episode, core, payload)
+    actions, pw = CO.selfplay(t, cfg, cg, s.S, s.moves, s.temperature, s.persist_tree, s.env_offset, s.dir_noise, s.dir_eps,
+                              s.root_noise, s.uniform01, core, payload, episode, nthreads)
+    res = Result({k: v.copy() for k, v in t.arrays().items()}, actions, pw)
+    res.stats = t.stats.copy()
+    return res
+
+
+def assert_trees_equal(a: dict, b: dict, what: str = ""):
+    """Bit-exact on integers / bytes; floats compared with == (so -0.0 == +0.0, NaN never expected)."""
+    assert set(a) == set(b), (what, set(a) ^ set(b))
+    for k in a:
+        x, y = np.asarray(a[k]), np.asarray(b[k])
+        assert x.shape == y.shape and x.dtype == y.dtype, (what, k, x.shape, y.shape, x.dtype, y.dtype)
+        if not np.array_equal(x, y):
+            bad = np.argwhere(x != y)
+            raise AssertionError(f"{what}: '{k}' differs at {len(bad)} places, first {bad[0].tolist()}: "
+                                 f"{x[tuple(bad[0])]!r} vs {y[tuple(bad[0])]!r}")
+
+
+def check_invariants(arr: dict):
+    """Structural invariants every tree must satisfy."""
+    nfi, parents, edge = arr["next_free_idx"], arr["parents"], arr["edge_map"]
+    B, N = parents.shape
+    for b in range(B):
+        k = int(nfi[b])
+        assert 0 <= k <= N
+        assert np.all(parents[b, k:] == -1) and np.all(edge[b, k:] == -1)
+        for name, v in arr.items():
+            if name in ("next_free_idx", "parents", "edge_map", "stats"):
+                continue
+            assert not np.any(v[b, k:]), (name, b)
+        if k == 0:
+            continue
+        assert parents[b, 0] == -1
+        idx = np.arange(1, k)
+        assert np.all(parents[b, 1:k] < idx) and np.all(parents[b, 1:k] >= 0)
+        e = edge[b, :k]
+        kids = e[e >= 0]
+        assert len(np.unique(kids)) == len(kids) == k - 1  # every non-root node is the child of exactly one edge
+        for i in range(1, k):
+            assert np.sum(e[parents[b, i]] == i) == 1

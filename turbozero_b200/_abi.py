@@ -1,0 +1,132 @@
+"""ctypes binding of include/tz_abi.h (libtz_b200.so) -- the only way this package reaches the kernels.
+
+There is NO fallback: if the CUDA library is missing or a call fails, an exception is raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+TZ_MAX_EMB = 24
+TZ_PATH_CAP = 32
+TZ_SEL_PUCT = 0
+TZ_SEL_MUZERO_PUCT = 1
+
+LIB_DIR = Path(__file__).resolve().parent / "lib"
+
+
+class TzTree(C.Structure):
+    _fields_ = [
+        ("B", C.c_int32), ("N", C.c_int32), ("F", C.c_int32), ("n_emb", C.c_int32),
+        ("next_free_idx", C.c_void_p), ("parents", C.c_void_p), ("edge_map", C.c_void_p),
+        ("n", C.c_void_p), ("p", C.c_void_p), ("q", C.c_void_p), ("r", C.c_void_p),
+        ("terminated", C.c_void_p),
+        ("emb", C.c_void_p * TZ_MAX_EMB),
+        ("emb_row_bytes", C.c_int64 * TZ_MAX_EMB),
+        ("stats", C.c_void_p),
+    ]
+
+
+class TzSearchCfg(C.Structure):
+    _fields_ = [
+        ("selector", C.c_int32), ("c", C.c_float), ("c1", C.c_float), ("c2", C.c_float),
+        ("epsilon", C.c_float), ("discount", C.c_float), ("weighted", C.c_int32),
+        ("inv_q_temperature", C.c_float), ("fma_backup", C.c_int32),
+    ]
+
+
+class TzWork(C.Structure):
+    _fields_ = [
+        ("parent", C.c_void_p), ("action", C.c_void_p),
+        ("emb_parent", C.c_void_p * TZ_MAX_EMB),
+        ("policy", C.c_void_p), ("value", C.c_void_p), ("terminated", C.c_void_p),
+        ("emb_new", C.c_void_p * TZ_MAX_EMB),
+        ("backprop_noise", C.c_void_p), ("path", C.c_void_p),
+    ]
+
+
+class TzSynthGame(C.Structure):
+    _fields_ = [
+        ("F", C.c_int32), ("payload_bytes", C.c_int32), ("rho256", C.c_int32), ("tau1024", C.c_int32),
+        ("max_depth", C.c_int32), ("seed", C.c_uint32),
+    ]
+
+
+class TzSynthCtx(C.Structure):
+    _fields_ = [("game", TzSynthGame), ("B", C.c_int32)]
+
+
+LEAF_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(TzWork), C.c_void_p)
+
+_P = C.POINTER
+_vp = C.c_void_p
+
+# name -> (restype, argtypes): every symbol include/tz_abi.h declares
+TZ_SYMBOLS = {
+    "tz_abi_version": (C.c_int, []),
+    "tz_strerror": (C.c_char_p, [C.c_int]),
+    "tz_launch_count": (C.c_uint64, []),
+    "tz_tree_init": (C.c_int, [_P(TzTree), _vp]),
+    "tz_set_root": (C.c_int, [_P(TzTree), _vp, _vp, _P(_vp), _vp]),
+    "tz_select": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), _vp]),
+    "tz_expand_backprop": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), _vp]),
+    "tz_expand_backprop_select": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), _vp]),
+    "tz_root_action": (C.c_int, [_P(TzTree), C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tz_reroot": (C.c_int, [_P(TzTree), _vp, _vp, C.c_int, _vp]),
+    "tz_search": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), C.c_int, _vp, _vp, _vp]),
+}
+
+TZ_SYNTH_SYMBOLS = {
+    "tz_synth_launch_count": (C.c_uint64, []),
+    "tz_synth_init_states": (C.c_int, [_P(TzSynthGame), C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
+    "tz_synth_root": (C.c_int, [_P(TzSynthGame), C.c_int, _vp, _vp, C.c_float, _vp, _vp, _vp]),
+    "tz_synth_leaf": (C.c_int, [_P(TzSynthGame), C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tz_synth_env_step": (C.c_int, [_P(TzSynthGame), C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "tz_synth_leaf_cb": (C.c_int, [_vp, C.c_int, _P(TzWork), _vp]),
+}
+
+
+class TzError(RuntimeError):
+    pass
+
+
+def _load(name: str, symbols) -> C.CDLL:
+    path = LIB_DIR / name
+    if not path.exists():
+        raise TzError(
+            f"{path} is missing: build it with `python -m turbozero_b200.build` (needs nvcc). "
+            "turbozero_b200 has no CPU or PyTorch fallback for the search kernels.")
+    lib = C.CDLL(str(path))
+    for sym, (res, args) in symbols.items():
+        fn = getattr(lib, sym)  # AttributeError here == ABI mismatch, which must be loud
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+_lib = None
+_synth = None
+
+
+def lib() -> C.CDLL:
+    """libtz_b200.so (loaded once)."""
+    global _lib
+    if _lib is None:
+        _lib = _load("libtz_b200.so", TZ_SYMBOLS)
+        if _lib.tz_abi_version() != 1:
+            raise TzError("libtz_b200.so ABI version mismatch")
+    return _lib
+
+
+def synth_lib() -> C.CDLL:
+    """libtz_synth.so: the synthetic game stand-in (bench / tests only)."""
+    global _synth
+    if _synth is None:
+        _synth = _load("libtz_synth.so", TZ_SYNTH_SYMBOLS)
+    return _synth
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().tz_strerror(rc)
+        raise TzError(f"{what} failed: {msg.decode() if msg else rc} (code {rc})")
