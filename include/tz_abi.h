@@ -126,9 +126,10 @@ int tz_root_action(const TzTree* t, float temperature, const float* noise, const
                    tz_stream_t stream);
 
 /* MCTS.step / MCTS.reset fused with the caller's select (core/common.py:89-94):
- * per tree, reset_flag[b] != 0 (or persist_tree == 0) -> Tree.reset (tree.py:272-278);
- * else Tree.get_subtree(action[b]) (tree.py:169-269).  reset_flag may be NULL (no resets);
- * action may be NULL only if persist_tree == 0 or every tree is reset.
+ * per tree, reset_flag[b] == 2 -> tree left untouched (common.py:91, reset=False);
+ * reset_flag[b] == 1 or persist_tree == 0 -> Tree.reset (tree.py:272-278);
+ * else Tree.get_subtree(action[b]) (tree.py:169-269), action clamped to [0,F) like an XLA gather.
+ * reset_flag may be NULL (all zero); action may be NULL only if persist_tree == 0.
  * Needs N*4 + <=64 KB of shared memory per CTA: N <= ~40000. */
 int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag, int persist_tree,
               tz_stream_t stream);

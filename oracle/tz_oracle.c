@@ -444,8 +444,12 @@ EXPORT int tzo_reroot(const TzTree* t, const int32_t* action, const uint8_t* res
 #pragma omp for schedule(static)
     for (int b = 0; b < t->B; ++b) {
       View v = view(t, b);
-      int do_reset = !persist_tree || (reset_flag && reset_flag[b]);
-      reroot(&v, do_reset ? 0 : action[b], do_reset, label, trans);
+      int flag = reset_flag ? reset_flag[b] : 0;
+      if (flag == 2) continue; /* untouched: common.py:91 `lambda s: s` */
+      int do_reset = !persist_tree || flag != 0;
+      int a = do_reset ? 0 : action[b];
+      a = a < 0 ? 0 : (a >= t->F ? t->F - 1 : a); /* XLA gather clamps */
+      reroot(&v, a, do_reset, label, trans);
     }
     free(label);
   }

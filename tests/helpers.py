@@ -10,6 +10,11 @@ from typing import List, Optional
 
 import numpy as np
 
+try:
+    import torch
+except Exception:  # pragma: no cover
+    torch = None
+
 from oracle import c_oracle as CO
 from oracle import mcts_numpy as M
 from oracle import synth_numpy as SN
@@ -207,3 +212,124 @@ def check_invariants(arr: dict):
         assert len(np.unique(kids)) == len(kids) == k - 1  # every non-root node is the child of exactly one edge
         for i in range(1, k):
             assert np.sum(e[parents[b, i]] == i) == 1
+
+
+# ----------------------------------------------------------------------------------------------------
+# CUDA path (only imported / called by the gpu tests)
+# ----------------------------------------------------------------------------------------------------
+def tree_to_numpy(tree) -> dict:
+    d = tree.data
+    out = {
+        "next_free_idx": tree.next_free_idx.cpu().numpy(),
+        "parents": tree.parents.cpu().numpy(),
+        "edge_map": tree.edge_map.cpu().numpy(),
+        "n": d.n.cpu().numpy(),
+        "p": d.p.cpu().numpy(),
+        "q": d.q.cpu().numpy(),
+        "terminated": d.terminated.cpu().numpy().astype(np.uint8),
+    }
+    if d.r is not None:
+        out["r"] = d.r.cpu().numpy()
+    for k, leaf in enumerate(tree._emb_leaves):
+        B, N = leaf.shape[:2]
+        out[f"emb{k}"] = leaf.contiguous().view(torch.uint8).reshape(B, N, -1).cpu().numpy() if leaf.dtype != torch.uint8 \
+            else leaf.reshape(B, N, -1).cpu().numpy()
+    return out
+
+
+def make_cuda_evaluator(s: Schedule, game):
+    import turbozero_b200 as tz
+
+    sel = tz.PUCTSelector(c=s.c) if s.selector == 0 else tz.MuZeroPUCTSelector()
+    base = tz.WeightedMCTS if s.weighted else tz.MCTS
+
+    class SynthRoot(base):
+        """Root evaluated by the synthetic stand-in so the policy bits equal the oracle's."""
+
+        def update_root(self, key, tree, root_embedding, params, root_metadata=None, dirichlet_noise=None, **kw):
+            pol, val = game.root_eval(root_embedding, dirichlet_noise, s.dir_eps)
+            return self._set_root(tree, pol, val, root_embedding)
+
+    kw = dict(eval_fn=None, action_selector=sel, branching_factor=game.F, max_nodes=s.N, num_iterations=s.S,
+              discount=s.discount, temperature=s.temperature, tiebreak_noise=s.tiebreak_noise, persist_tree=s.persist_tree)
+    if s.weighted:
+        kw["q_temperature"] = s.q_temperature
+    ev = SynthRoot(**kw)
+    ev.fma_backup = s.fma_backup
+    return ev
+
+
+def run_cuda_api(s: Schedule, fused: bool = True, snapshots: bool = False) -> Result:
+    """The CUDA path through the Python mirror of the reference API (MCTS.evaluate / iterate / step)."""
+    import torch
+    from turbozero_b200.synthetic import SyntheticGame
+
+    g = s.game
+    game = SyntheticGame(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
+    ev = make_cuda_evaluator(s, game)
+    B, F = s.B, g.F
+    tree = ev.init_batched(B, game.template_embedding(), stats=True)
+    state, episode = game.init_states(B, s.env_offset)
+    reset_flag = torch.zeros((B,), dtype=torch.uint8, device="cuda")
+    dev = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    actions = np.zeros((s.moves, B), np.int32)
+    pw = np.zeros((s.moves, B, F), np.float32)
+    snaps = [] if snapshots else None
+    for m in range(s.moves):
+        dn = None if s.dir_noise is None else dev(s.dir_noise[m])
+        rn, u01 = dev(s.root_noise[m]), dev(s.uniform01[m])
+        bpn = None if s.bp_noise is None else dev(s.bp_noise[m])
+        if fused:
+            out = ev.evaluate(None, tree, state, None, None, None, leaf_fn=game.leaf_fn, root_noise=rn, uniform01=u01,
+                              backprop_noise=bpn, dirichlet_noise=dn)
+            act, pwm = out.action, out.policy_weights
+        else:
+            ev.update_root(None, tree, state, None, dirichlet_noise=dn)
+            for it in range(s.S):
+                ev.iterate(None, tree, None, None, leaf_fn=game.leaf_fn, backprop_noise=None if bpn is None else bpn[it])
+            act, pwm = ev.sample_root_action(None, tree, root_noise=rn, uniform01=u01)
+        actions[m], pw[m] = act.cpu().numpy(), pwm.cpu().numpy()
+        if snapshots:
+            snaps.append(tree_to_numpy(tree))
+        game.env_step(state, act, episode, reset_flag, s.env_offset)
+        ev.step(tree, act, reset_mask=reset_flag)
+    res = Result(tree_to_numpy(tree), actions, pw, snaps)
+    res.stats = tree.stats.cpu().numpy().astype(np.uint64)
+    return res
+
+
+def run_cuda_selfplay(s: Schedule, use_path: bool = True, graph: bool = False) -> Result:
+    """The CUDA path with the whole simulation loop inside the C-ABI (tz_search + tz_synth_leaf_cb)."""
+    import torch
+    from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay
+
+    g = s.game
+    game = SyntheticGame(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
+    ev = make_cuda_evaluator(s, game)
+    sp = SyntheticSelfPlay(game, ev, s.B, env_offset=s.env_offset, dirichlet=s.dirichlet, use_path=use_path)
+    sp.dir_eps = s.dir_eps
+    actions = np.zeros((s.moves, s.B), np.int32)
+    pw = np.zeros((s.moves, s.B, g.F), np.float32)
+    cg = None
+    for m in range(s.moves):
+        if s.dir_noise is not None:
+            sp.dir_noise.copy_(torch.from_numpy(s.dir_noise[m]))
+        sp.root_noise.copy_(torch.from_numpy(s.root_noise[m]))
+        sp.uniform01.copy_(torch.from_numpy(s.uniform01[m]))
+        if graph:
+            if cg is None:
+                # capture one move; capture does not execute, so replay it for move 0 as well
+                side = torch.cuda.Stream()
+                side.wait_stream(torch.cuda.current_stream())
+                cg = torch.cuda.CUDAGraph()
+                with torch.cuda.stream(side):
+                    with torch.cuda.graph(cg, stream=side):
+                        sp.move()
+                torch.cuda.current_stream().wait_stream(side)
+            cg.replay()
+        else:
+            sp.move()
+        actions[m], pw[m] = sp.action.cpu().numpy(), sp.policy_weights.cpu().numpy()
+    res = Result(tree_to_numpy(sp.tree), actions, pw)
+    res.stats = sp.tree.stats.cpu().numpy().astype(np.uint64)
+    return res

@@ -1,0 +1,87 @@
+"""GPU parity: the CUDA path (through the C-ABI) against the C oracle on identical seeded inputs.
+Integers / bytes bit-exact, floats equal (== ; the only slack is the sign of zero)."""
+import numpy as np
+import pytest
+
+from helpers import (Schedule, assert_trees_equal, check_invariants, run_c_stepwise, run_c_treemajor, run_cuda_api,
+                     run_cuda_selfplay)
+from oracle import synth_numpy as SN
+
+pytestmark = pytest.mark.gpu
+
+
+def G(**kw):
+    return SN.SynthGame(**kw)
+
+
+CASES = {
+    "ttt_T0": dict(game=G(F=9, payload_bytes=7, rho256=154, tau1024=40, max_depth=9, seed=1), B=5, N=12, S=30, moves=6, temperature=0.0),
+    "ttt_cfg1": dict(game=SN.make_game("tic_tac_toe", 1001), B=32, N=128, S=64, moves=5, temperature=1.0),
+    "c4": dict(game=G(F=7, payload_bytes=32, rho256=230, tau1024=12, max_depth=42, seed=2), B=9, N=64, S=40, moves=4, temperature=1.0),
+    "othello_weighted": dict(game=G(F=65, payload_bytes=0, rho256=38, tau1024=6, max_depth=60, seed=3), B=4, N=50, S=30, moves=3,
+                             temperature=1.0, weighted=True),
+    "othello_weighted_T05": dict(game=G(F=65, payload_bytes=5, rho256=38, tau1024=6, max_depth=60, seed=3), B=4, N=50, S=30,
+                                 moves=3, temperature=0.5, weighted=True, q_temperature=0.5),
+    "weighted_qT0": dict(game=G(F=33, payload_bytes=5, rho256=100, tau1024=6, max_depth=60, seed=4), B=3, N=50, S=30, moves=3,
+                         temperature=1.0, weighted=True, q_temperature=0.0),
+    "go_muzero": dict(game=G(F=82, payload_bytes=48, rho256=205, tau1024=2, max_depth=120, seed=5), B=3, N=80, S=60, moves=3,
+                      temperature=1.0, selector=1),
+    "g2048_pos_discount": dict(game=G(F=4, payload_bytes=16, rho256=218, tau1024=4, max_depth=200, seed=6), B=6, N=40, S=30,
+                               moves=5, temperature=1.0, discount=1.0, dirichlet=False),
+    "no_persist": dict(game=G(F=7, payload_bytes=3, rho256=230, tau1024=100, max_depth=6, seed=7), B=4, N=64, S=40, moves=6,
+                       temperature=1.0, persist_tree=False),
+    "deep_discount09": dict(game=G(F=5, payload_bytes=3, rho256=230, tau1024=0, max_depth=100, seed=8), B=3, N=200, S=150,
+                            moves=3, temperature=1.0, discount=0.9, c=2.5),
+    "fma": dict(game=G(F=7, payload_bytes=16, rho256=230, tau1024=12, max_depth=42, seed=9), B=8, N=64, S=48, moves=4,
+                temperature=1.0, fma_backup=True),
+    "wide_F300": dict(game=G(F=300, payload_bytes=20, rho256=128, tau1024=2, max_depth=50, seed=10), B=3, N=70, S=50, moves=3,
+                      temperature=1.0),
+    "very_deep": dict(game=G(F=2, payload_bytes=4, rho256=0, tau1024=0, max_depth=1000, seed=12), B=3, N=120, S=100, moves=2,
+                      temperature=1.0, discount=0.97),
+}
+
+
+def _compare(a, b, what):
+    assert np.array_equal(a.actions, b.actions), what
+    assert np.array_equal(a.pw, b.pw), what
+    assert_trees_equal(a.arrays, b.arrays, what)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_api_fused_vs_oracle(name):
+    s = Schedule(**CASES[name])
+    ref = run_c_stepwise(s, snapshots=True)
+    got = run_cuda_api(s, fused=True, snapshots=True)
+    for m, (x, y) in enumerate(zip(ref.snapshots, got.snapshots)):
+        assert_trees_equal(x, y, f"{name}: after search of move {m}")
+    _compare(ref, got, name)
+    assert np.array_equal(ref.stats, got.stats)
+    check_invariants(got.arrays)
+
+
+@pytest.mark.parametrize("name", ["ttt_T0", "c4", "othello_weighted", "weighted_qT0", "very_deep"])
+def test_api_unfused_vs_oracle(name):
+    s = Schedule(**CASES[name])
+    _compare(run_c_stepwise(s), run_cuda_api(s, fused=False), name)
+
+
+@pytest.mark.parametrize("name", [n for n in CASES if n != "weighted_qT0"])
+@pytest.mark.parametrize("use_path", [True, False])
+def test_c_search_loop_vs_oracle(name, use_path):
+    s = Schedule(**CASES[name])
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, use_path=use_path), name)
+
+
+@pytest.mark.parametrize("name", ["ttt_cfg1", "c4", "othello_weighted"])
+def test_graph_replay_vs_oracle(name):
+    s = Schedule(**CASES[name])
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), name)
+
+
+def test_connect_four_full_size():
+    """BASELINE.json configs[1] at full size: 1024 envs x 128 simulations, N = 256, subtree persistence on."""
+    s = Schedule(game=SN.make_game("connect_four", 2000), B=1024, N=256, S=128, moves=4, temperature=1.0)
+    ref = run_c_treemajor(s)
+    got = run_cuda_selfplay(s, graph=True)
+    _compare(ref, got, "connect_four full")
+    check_invariants({k: v[:64] for k, v in got.arrays.items()})

@@ -1,0 +1,17 @@
+"""turbozero_b200 -- turbozero's batched MCTS hot path as hand-written sm_100a CUDA kernels behind the
+reference's own Evaluator / MCTS API.  See DESIGN.md and INTEGRATION.md."""
+from .action_selection import MCTSActionSelector, MuZeroPUCTSelector, PUCTSelector, normalize_q_values
+from .alphazero import AlphaZero
+from .common import partition, shard_slice, step_env_and_evaluator
+from .evaluator import EvalOutput, Evaluator
+from .mcts import MCTS, MCTSOutput, TraversalState
+from .trees import MCTSNode, MCTSTree, Tree, WeightedMCTSNode, init_tree
+from .types import StepMetadata
+from .weighted_mcts import WeightedMCTS
+
+__all__ = [
+    "MCTS", "WeightedMCTS", "AlphaZero", "MCTSOutput", "TraversalState", "Evaluator", "EvalOutput",
+    "MCTSActionSelector", "PUCTSelector", "MuZeroPUCTSelector", "normalize_q_values",
+    "Tree", "MCTSTree", "MCTSNode", "WeightedMCTSNode", "init_tree", "StepMetadata",
+    "partition", "shard_slice", "step_env_and_evaluator",
+]

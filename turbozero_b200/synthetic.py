@@ -1,0 +1,178 @@
+"""Device-side synthetic game (libtz_synth.so, include/tz_synth.h) wrapped for PyTorch.
+
+Stand-in for the user's pgx environment + network, which cannot run in this image.  Used by bench.py, the GPU
+parity tests and smoke(); it is not part of the product path (the search never depends on it).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _abi
+from .trees import Tree, _stream_ptr
+
+# name: (F, payload_bytes, rho256, tau1024, max_depth): shapes of BASELINE.json's pgx games
+GAMES = {
+    "tic_tac_toe": (9, 72, 154, 40, 9),
+    "connect_four": (7, 272, 230, 12, 42),
+    "othello": (65, 448, 38, 6, 60),
+    "go_9x9": (82, 4080, 205, 2, 120),
+    "2048": (4, 560, 218, 4, 200),
+}
+
+
+@dataclass
+class SyntheticGame:
+    F: int
+    payload_bytes: int
+    rho256: int
+    tau1024: int
+    max_depth: int
+    seed: int
+
+    @classmethod
+    def named(cls, name: str, seed: int) -> "SyntheticGame":
+        F, P, rho, tau, D = GAMES[name]
+        return cls(F, P, rho, tau, D, seed)
+
+    def __post_init__(self):
+        self._c = _abi.TzSynthGame(F=self.F, payload_bytes=self.payload_bytes, rho256=self.rho256, tau1024=self.tau1024,
+                                   max_depth=self.max_depth, seed=self.seed)
+        self._out: Dict[int, tuple] = {}
+
+    @property
+    def emb_bytes(self) -> int:
+        return 16 + self.payload_bytes
+
+    def template_embedding(self) -> Dict[str, torch.Tensor]:
+        t = {"core": torch.zeros(4, dtype=torch.int32)}
+        if self.payload_bytes > 0:
+            t["payload"] = torch.zeros(self.payload_bytes, dtype=torch.uint8)
+        return t
+
+    # --- env_init_fn ---
+    def init_states(self, B: int, env_offset: int = 0, episode: Optional[torch.Tensor] = None, device="cuda"):
+        episode = torch.zeros((B,), dtype=torch.int32, device=device) if episode is None else episode
+        state = {"core": torch.empty((B, 4), dtype=torch.int32, device=device)}
+        if self.payload_bytes > 0:
+            state["payload"] = torch.empty((B, self.payload_bytes), dtype=torch.uint8, device=device)
+        _abi.check(_abi.synth_lib().tz_synth_init_states(C.byref(self._c), B, env_offset, episode.data_ptr(),
+                                                         state["core"].data_ptr(), self._pay(state), _stream_ptr()),
+                   "tz_synth_init_states")
+        return state, episode
+
+    @staticmethod
+    def _pay(state) -> Optional[int]:
+        return state["payload"].data_ptr() if "payload" in state else None
+
+    # --- root evaluation (mcts.py:137-138 / alphazero.py:57-76) ---
+    def root_eval(self, state, dir_noise: Optional[torch.Tensor] = None, dir_eps: float = 0.25,
+                  out: Optional[Tuple[torch.Tensor, torch.Tensor]] = None):
+        B, dev = state["core"].shape[0], state["core"].device
+        pol, val = out if out is not None else (torch.empty((B, self.F), dtype=torch.float32, device=dev),
+                                                torch.empty((B,), dtype=torch.float32, device=dev))
+        _abi.check(_abi.synth_lib().tz_synth_root(C.byref(self._c), B, state["core"].data_ptr(),
+                                                  None if dir_noise is None else dir_noise.data_ptr(), dir_eps,
+                                                  pol.data_ptr(), val.data_ptr(), _stream_ptr()), "tz_synth_root")
+        return pol, val
+
+    # --- fused leaf_fn (env_step_fn + eval_fn + mcts.py:166-172) ---
+    def leaf_fn(self, parent_emb, action: torch.Tensor):
+        B, dev = action.shape[0], action.device
+        bufs = self._out.get(B)
+        if bufs is None:
+            new = {"core": torch.empty((B, 4), dtype=torch.int32, device=dev)}
+            if self.payload_bytes > 0:
+                new["payload"] = torch.empty((B, self.payload_bytes), dtype=torch.uint8, device=dev)
+            bufs = (new, torch.empty((B, self.F), dtype=torch.float32, device=dev),
+                    torch.empty((B,), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.uint8, device=dev))
+            self._out[B] = bufs
+        new, pol, val, term = bufs
+        _abi.check(_abi.synth_lib().tz_synth_leaf(C.byref(self._c), B, parent_emb["core"].data_ptr(), action.data_ptr(),
+                                                  pol.data_ptr(), val.data_ptr(), term.data_ptr(), new["core"].data_ptr(),
+                                                  self._pay(new), _stream_ptr()), "tz_synth_leaf")
+        return new, pol, val, term
+
+    # --- real environment step after a move (common.py:82-99) ---
+    def env_step(self, state, action: torch.Tensor, episode: torch.Tensor, reset_flag: torch.Tensor, env_offset: int = 0):
+        B = action.shape[0]
+        _abi.check(_abi.synth_lib().tz_synth_env_step(C.byref(self._c), B, env_offset, action.data_ptr(),
+                                                      state["core"].data_ptr(), self._pay(state), episode.data_ptr(),
+                                                      reset_flag.data_ptr(), _stream_ptr()), "tz_synth_env_step")
+        return state
+
+    def leaf_callback(self, B: int):
+        """(function pointer, user pointer, keepalive) for tz_search: the whole simulation loop stays in C."""
+        ctx = _abi.TzSynthCtx(game=self._c, B=B)
+        fn = C.cast(_abi.synth_lib().tz_synth_leaf_cb, C.c_void_p)
+        return fn, C.cast(C.pointer(ctx), C.c_void_p), ctx
+
+
+class SyntheticSelfPlay:
+    """Self-play of B synthetic games through the C-ABI only (no per-simulation Python): per move
+    tz_synth_root -> tz_set_root -> tz_search(tz_synth_leaf_cb) -> tz_root_action -> tz_synth_env_step -> tz_reroot.
+    This is `step_env_and_evaluator` (core/common.py:32-103) with the user's functions replaced by the stand-in.
+    All buffers are static, so one move is capturable in a CUDA graph."""
+
+    def __init__(self, game: SyntheticGame, evaluator, B: int, *, env_offset: int = 0, dirichlet: bool = True,
+                 device="cuda", stats: bool = True, use_path: bool = True):
+        self.game, self.ev, self.B, self.env_offset = game, evaluator, B, env_offset
+        self.dev = torch.device(device)
+        self.tree: Tree = evaluator.init_batched(B, game.template_embedding(), device=device, stats=stats)
+        self.state, self.episode = game.init_states(B, env_offset, device=device)
+        F = game.F
+        f32, dev = torch.float32, self.dev
+        self.root_policy = torch.empty((B, F), dtype=f32, device=dev)
+        self.root_value = torch.empty((B,), dtype=f32, device=dev)
+        self.dir_noise = torch.empty((B, F), dtype=f32, device=dev) if dirichlet else None
+        self.root_noise = torch.zeros((B, F), dtype=f32, device=dev)
+        self.uniform01 = torch.zeros((B,), dtype=f32, device=dev)
+        self.action = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.policy_weights = torch.zeros((B, F), dtype=f32, device=dev)
+        self.reset_flag = torch.zeros((B,), dtype=torch.uint8, device=dev)
+        # TzWork with static leaf buffers
+        self.w_parent = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.w_action = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self.w_path = torch.zeros((B, _abi.TZ_PATH_CAP + 1), dtype=torch.int32, device=dev) if use_path else None
+        self.w_policy = torch.empty((B, F), dtype=f32, device=dev)
+        self.w_value = torch.empty((B,), dtype=f32, device=dev)
+        self.w_term = torch.empty((B,), dtype=torch.uint8, device=dev)
+        leaves = [torch.empty((B, 4), dtype=torch.int32, device=dev)]
+        leaves2 = [torch.empty((B, 4), dtype=torch.int32, device=dev)]
+        if game.payload_bytes > 0:
+            leaves.append(torch.empty((B, game.payload_bytes), dtype=torch.uint8, device=dev))
+            leaves2.append(torch.empty((B, game.payload_bytes), dtype=torch.uint8, device=dev))
+        self.w_emb_parent, self.w_emb_new = leaves, leaves2
+        w = _abi.TzWork()
+        w.parent, w.action = self.w_parent.data_ptr(), self.w_action.data_ptr()
+        w.path = self.w_path.data_ptr() if use_path else None
+        w.policy, w.value, w.terminated = self.w_policy.data_ptr(), self.w_value.data_ptr(), self.w_term.data_ptr()
+        for k in range(len(leaves)):
+            w.emb_parent[k] = leaves[k].data_ptr()
+            w.emb_new[k] = leaves2[k].data_ptr()
+        self.work = w
+        self.cfg = evaluator._cfg()
+        self._cb = game.leaf_callback(B)
+        self.dir_eps = getattr(evaluator, "dirichlet_epsilon", 0.25)
+
+    def launches_per_move(self) -> int:
+        S = self.ev.num_iterations
+        return 1 + 1 + (1 + S + S) + 1 + 1 + 1  # root, set_root, select + S leaf + S expand, root_action, env_step, reroot
+
+    def move(self) -> None:
+        """One self-play move for all B games; enqueues only (no sync)."""
+        lib, ev, stream = _abi.lib(), self.ev, _stream_ptr()
+        ts = self.tree.struct()
+        self.game.root_eval(self.state, self.dir_noise, self.dir_eps, out=(self.root_policy, self.root_value))
+        ptrs = (C.c_void_p * 2)(self.state["core"].data_ptr(), SyntheticGame._pay(self.state))
+        _abi.check(lib.tz_set_root(C.byref(ts), self.root_policy.data_ptr(), self.root_value.data_ptr(), ptrs, stream), "tz_set_root")
+        fn, user, _keep = self._cb
+        _abi.check(lib.tz_search(C.byref(ts), C.byref(self.cfg), C.byref(self.work), ev.num_iterations, fn, user, stream), "tz_search")
+        _abi.check(lib.tz_root_action(C.byref(ts), float(ev.temperature), self.root_noise.data_ptr(), self.uniform01.data_ptr(),
+                                      None, self.policy_weights.data_ptr(), None, self.action.data_ptr(), stream), "tz_root_action")
+        self.game.env_step(self.state, self.action, self.episode, self.reset_flag, self.env_offset)
+        _abi.check(lib.tz_reroot(C.byref(ts), self.action.data_ptr(), self.reset_flag.data_ptr(), 1 if ev.persist_tree else 0,
+                                 stream), "tz_reroot")
