@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""bench.py -- MCTS simulations/sec of the batched search hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+
+A STEP is one self-play move of every env on this rank: root evaluation + set_root, S simulations
+(select -> leaf -> expand+backprop), root-action sampling, env step, and subtree re-rooting (or reset where the
+episode ended) -- i.e. `step_env_and_evaluator` of the reference (core/common.py:32-103) with the user's pgx env and
+network replaced by the synthetic stand-in (pgx / JAX are not installable here).
+
+Default workload = BASELINE.json configs[1]: connect_four shape, 1024 envs x 128 simulations, max_nodes 256, subtree
+persistence on, one B200.  With --gpus N every rank owns its own 1024 envs (independent tree batches, no collective
+in the search) => weak scaling; `value` is the whole-job aggregate.
+
+Legs of the default arm (all in one JSON line):
+  value        device-resident inputs, one CUDA-graph replay per step, per-step CUDA events, L2 flushed between steps
+  e2e          the public Python API (MCTS.evaluate + MCTS.step, captured by the user in a CUDA graph) with per-step
+               H2D copies of the step's random inputs from pinned memory and a D2H read of actions + policy weights
+  roofline     the per-simulation kernel (k_sim: expand+backprop+select) timed by CUDA events recorded around every
+               launch on the launching stream; achieved = algorithmic bytes / duration  vs measured HBM peak
+  cpu_baseline the CPU oracle (C restatement, OpenMP over trees) on a bounded sample of the same workload (rank 0, N=1)
+
+`--impl reference`: the reference's algorithm on the host CPU only (the oracle port; the real reference needs JAX,
+which is absent), all host threads, same config / metric.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+METRIC = "mcts_simulations_per_sec"
+UNIT = "simulations/s"
+
+# name -> (synthetic game shape, envs per GPU, simulations, max_nodes, weighted, discount, description)
+WORKLOADS = {
+    "cfg1": ("tic_tac_toe", 32, 64, 128, False, -1.0, "tic_tac_toe 32 envs x 64 sims (configs[0])"),
+    "cfg2": ("connect_four", 1024, 128, 256, False, -1.0, "connect_four 1024 envs x 128 sims, persist_tree (configs[1])"),
+    "cfg3": ("othello", 512, 200, 400, True, -1.0, "othello 4096 envs / 8 GPUs x 200 sims, WeightedMCTS (configs[2])"),
+    "cfg4": ("go_9x9", 1024, 800, 1600, False, -1.0, "go_9x9 8192 envs / 8 GPUs x 800 sims (configs[3])"),
+    "cfg5": ("2048", 2048, 100, 200, False, 1.0, "2048 16384 envs / 8 GPUs x 100 sims, discount +1 (configs[4])"),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=24)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--skip-e2e", action="store_true")
+    ap.add_argument("--skip-roofline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    return ap.parse_args()
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def host_inputs(rng, steps, B, F, alpha=0.3):
+    dn = rng.dirichlet([alpha] * F, size=(steps, B)).astype(np.float32)
+    rn = (rng.random((steps, B, F), dtype=np.float32) * np.float32(1e-8)).astype(np.float32)
+    u = rng.random((steps, B), dtype=np.float32)
+    return dn, rn, u
+
+
+def algorithmic_bytes(levels, sims, F, E, weighted):
+    """per simulation L*(16F+28) + 8F + 4E + 25 bytes (weighted: + L*(12F+4))."""
+    per_level = 16 * F + 28 + ((12 * F + 4) if weighted else 0)
+    return levels * per_level + sims * (8 * F + 4 * E + 25)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm: the reference's algorithm on the host CPU (oracle port; JAX is not installable)
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_selfplay_setup(wl, B, env_offset, seed):
+    from oracle import c_oracle as CO
+    from oracle import synth_numpy as SN
+
+    name, _, S, N, weighted, discount, _ = WORKLOADS[wl]
+    g = SN.make_game(name, seed)
+    cg = CO.make_game(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
+    cfg = CO.make_cfg(discount=discount, weighted=weighted)
+    t = CO.HostTrees(B, N, g.F, g.emb_row_bytes, weighted=weighted)
+    episode = np.zeros((B,), np.int32)
+    core = np.zeros((B, 4), np.int32)
+    payload = np.zeros((B, g.payload_bytes), np.uint8) if g.payload_bytes > 0 else None
+    CO.synth_init_states(cg, B, env_offset, episode, core, payload)
+    return CO, g, cg, cfg, t, episode, core, payload
+
+
+def cpu_moves(CO, cg, cfg, t, S, moves, dn, rn, u, core, payload, episode, nthreads):
+    t0 = time.perf_counter()
+    CO.selfplay(t, cfg, cg, S, moves, 1.0, True, 0, dn, 0.25, rn, u, core, payload, episode, nthreads)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.workload
+    name, B0, S, N, weighted, discount, desc = WORKLOADS[wl]
+    B = args.envs or B0
+    CO, g, cg, cfg, t, episode, core, payload = cpu_selfplay_setup(wl, B, 0, 1000)
+    threads = CO.num_threads()
+    rng = np.random.default_rng(1)
+    total = max(args.warmup, 1) + args.steps
+    dn, rn, u = host_inputs(rng, total, B, g.F)
+    warm, i = 0.0, 0
+    while i < args.warmup or warm < 2.0:  # at least W moves and 2 s: shared host cores ramp up slowly
+        j = min(i, args.warmup - 1) if args.warmup > 0 else 0
+        warm += cpu_moves(CO, cg, cfg, t, S, 1, dn[j:j + 1], rn[j:j + 1], u[j:j + 1], core, payload, episode, threads)
+        i += 1
+    t0 = time.perf_counter()
+    for i in range(total - args.steps, total):
+        cpu_moves(CO, cg, cfg, t, S, 1, dn[i:i + 1], rn[i:i + 1], u[i:i + 1], core, payload, episode, threads)
+    dt = time.perf_counter() - t0
+    value = B * S * args.steps / dt
+    sample = f"{args.steps} moves of {B} envs x {S} sims (full per-GPU workload), tree-major C oracle"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+        "config": {"workload": desc, "envs": B, "simulations": S, "max_nodes": N, "branching_factor": g.F,
+                   "embedding_bytes": g.payload_bytes + 16, "note": "reference algorithm on host CPU via the oracle port "
+                   "(oracle/tz_oracle.c); the reference itself needs JAX, which is not installable in this image"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# native arm
+# ------------------------------------------------------------------------------------------------------------------
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+
+    import turbozero_b200 as tz
+    from turbozero_b200 import _abi
+    from turbozero_b200.common import step_env_and_evaluator
+    from turbozero_b200.synthetic import SyntheticEnv, SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (native arm) needs a CUDA device; there is no CPU fallback for the search kernels")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    wl = args.workload
+    name, B0, S, N, weighted, discount, desc = WORKLOADS[wl]
+    B = args.envs or B0
+    K, W = args.steps, args.warmup
+    seed = 1000 + rank
+    game = SyntheticGame.named(name, seed)
+    F, E = game.F, game.emb_bytes
+    base = tz.WeightedMCTS if weighted else tz.MCTS
+
+    def new_eval():
+        return make_synthetic_evaluator(base, game, action_selector=tz.PUCTSelector(), max_nodes=N, num_iterations=S,
+                                        discount=discount, temperature=1.0)
+
+    lib, slib = _abi.lib(), _abi.synth_lib()
+
+    def launches():
+        return lib.tz_launch_count() + slib.tz_synth_launch_count()
+
+    rng = np.random.default_rng(seed)
+    total = W + K
+    dn_h, rn_h, u_h = host_inputs(rng, total, B, F)
+    flush_buf = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=dev)
+
+    def flush():
+        if flush_buf is not None:
+            flush_buf.fill_(1)
+
+    # ---------------- leg 1: device-resident inputs, whole move in the C-ABI (tz_search + leaf callback) ----------
+    ev = new_eval()
+    sp = SyntheticSelfPlay(game, ev, B, env_offset=rank * B, dirichlet=True, device=dev, stats=True)
+    dn_d, rn_d, u_d = (torch.from_numpy(x).to(dev) for x in (dn_h, rn_h, u_h))
+
+    def load_inputs(i):
+        sp.dir_noise.copy_(dn_d[i], non_blocking=True)
+        sp.root_noise.copy_(rn_d[i], non_blocking=True)
+        sp.uniform01.copy_(u_d[i], non_blocking=True)
+
+    l0 = launches()
+    sp.move()  # un-captured first move: loads modules, sizes caches
+    torch.cuda.synchronize()
+    launches_per_move = launches() - l0
+    if args.no_graph:
+        step = sp.move
+    else:
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        cg = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(cg, stream=side):
+                sp.move()
+        torch.cuda.current_stream().wait_stream(side)
+        step = cg.replay
+    for i in range(W):
+        load_inputs(i)
+        step()
+    torch.cuda.synchronize()
+    stats0 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(K):
+        load_inputs(W + i)
+        flush()
+        evs[i][0].record()
+        step()
+        evs[i][1].record()
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    stats1 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
+    d_stats = stats1 - stats0
+    levels_per_sim = float(d_stats[0]) / max(float(d_stats[1]), 1.0)
+    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    max_ms = float(t_ms.item())
+    value = world * B * S * K / (max_ms * 1e-3)
+
+    # ---------------- leg 2: roofline of the dominant kernel (k_sim), CUDA events around every launch --------------
+    roofline = None
+    if not args.skip_roofline:
+        peak, peak_src = measured_peaks()
+        moves_r = 2
+        ends = [[torch.cuda.Event(enable_timing=True) for _ in range(S)] for _ in range(moves_r)]
+        starts = [[torch.cuda.Event(enable_timing=True) for _ in range(S)] for _ in range(moves_r)]
+        cur = {"m": 0}
+        leaf_c = slib.tz_synth_leaf_cb
+        user_ptr = sp._cb[1]
+
+        def timed_leaf(user, sim, w, stream):
+            m = cur["m"]
+            ends[m][sim].record()  # closes the k_sim launch enqueued just before this callback
+            rc = leaf_c(user_ptr, sim, w, stream)
+            starts[m][sim].record()  # opens the k_sim launch enqueued right after
+            return rc
+
+        cb = _abi.LEAF_FN(timed_leaf)
+        saved = sp._cb
+        sp._cb = (C.cast(cb, C.c_void_p), user_ptr, saved[2])
+        st0 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
+        flush()
+        for m in range(moves_r):
+            cur["m"] = m
+            load_inputs(W + m)
+            sp.move()
+        torch.cuda.synchronize()
+        sp._cb = saved
+        st1 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
+        durs = []
+        for m in range(moves_r):
+            for s_ in range(S - 1):  # fused launches: expand+backprop of sim s_, select of sim s_+1
+                durs.append(starts[m][s_].elapsed_time(ends[m][s_ + 1]))
+        dur_ms = sum(durs) / len(durs)
+        dl, ds = int(st1[0] - st0[0]), int(st1[1] - st0[1])
+        bytes_total = algorithmic_bytes(dl, ds, F, E, weighted)
+        bytes_per_launch = bytes_total / max(ds // B, 1)
+        achieved = bytes_per_launch / (dur_ms * 1e-3) / 1e9
+        roofline = {"bound": "hbm", "kernel": "k_sim (expand+backprop of simulation i fused with select of i+1)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "levels_per_sim": dl / max(ds, 1), "note": "working set (trees of 1024 envs) fits the 126 MB L2: "
+                    "the kernel is L2-latency bound pointer chasing, not HBM-bandwidth bound"}
+
+    # ---------------- leg 3: e2e through the public Python API with host buffers -----------------------------------
+    e2e = None
+    if not args.skip_e2e:
+        ev2 = new_eval()
+        env = SyntheticEnv(game, B, env_offset=rank * B, device=dev)
+        tree2 = ev2.init_batched(B, game.template_embedding(), device=dev)
+        s_dn = torch.empty((B, F), dtype=torch.float32, device=dev)
+        s_rn = torch.empty((B, F), dtype=torch.float32, device=dev)
+        s_u = torch.empty((B,), dtype=torch.float32, device=dev)
+        out_box = {}
+
+        def user_step():
+            out, _, _, _, _, _ = step_env_and_evaluator(
+                key=None, env_state=env.state, env_state_metadata=env.metadata(), eval_state=tree2, params=None,
+                evaluator=ev2, env_step_fn=env.env_step_fn, env_init_fn=None, max_steps=1 << 30,
+                leaf_fn=game.leaf_fn, root_noise=s_rn, uniform01=s_u, dirichlet_noise=s_dn)
+            out_box["action"], out_box["pw"] = out.action, out.policy_weights
+
+        pin = lambda a: torch.from_numpy(a).pin_memory()
+        dn_p, rn_p, u_p = pin(dn_h), pin(rn_h), pin(u_h)
+        act_p = torch.empty((B,), dtype=torch.int32).pin_memory()
+        pw_p = torch.empty((B, F), dtype=torch.float32).pin_memory()
+
+        def h2d(i):
+            s_dn.copy_(dn_p[i], non_blocking=True)
+            s_rn.copy_(rn_p[i], non_blocking=True)
+            s_u.copy_(u_p[i], non_blocking=True)
+
+        h2d(0)
+        l0 = launches()
+        user_step()
+        torch.cuda.synchronize()
+        api_launches = launches() - l0
+        if args.no_graph:
+            api_step = user_step
+        else:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            cg2 = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(cg2, stream=side):
+                    user_step()
+            torch.cuda.current_stream().wait_stream(side)
+            api_step = cg2.replay
+
+        def e2e_step(i):
+            h2d(i)
+            api_step()
+            act_p.copy_(out_box["action"], non_blocking=True)
+            pw_p.copy_(out_box["pw"], non_blocking=True)
+            torch.cuda.synchronize()  # the host needs the actions before it can go on
+
+        for i in range(W):
+            e2e_step(i)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for i in range(K):
+            e2e_step(W + i)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        barrier()
+        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B * S * K / float(t_e.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(2 * B * F * 4 + B * 4), "d2h_bytes_per_step": int(B * 4 + B * F * 4),
+               "ms_per_step": float(t_e.item()) / K * 1e3,
+               "api": "step_env_and_evaluator(MCTS.evaluate + MCTS.step) captured in a CUDA graph by the caller; "
+                      "host wall clock incl. pinned H2D of the step's noise inputs and D2H of actions + policy weights",
+               "launches_per_step": int(api_launches)}
+
+    # ---------------- leg 4: CPU baseline (oracle port) on a bounded sample ---------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.skip_cpu:
+        CO, g, cgm, cfg, t, episode, core, payload = cpu_selfplay_setup(wl, B, 0, seed)
+        threads = CO.num_threads()
+        dnc, rnc, uc = host_inputs(np.random.default_rng(2), 1, B, F)
+        warm = 0.0
+        while warm < 2.0:  # host cores of a shared box take a second or two to ramp up / schedule all threads
+            warm += cpu_moves(CO, cgm, cfg, t, S, 1, dnc, rnc, uc, core, payload, episode, threads)
+        moves_done, spent = 0, 0.0
+        while spent < args.cpu_seconds and moves_done < 4096:
+            spent += cpu_moves(CO, cgm, cfg, t, S, 1, dnc, rnc, uc, core, payload, episode, threads)
+            moves_done += 1
+        cpu = {"value": B * S * moves_done / spent, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{moves_done} moves of {B} envs x {S} sims ({spent:.1f} s), tree-major C oracle, OpenMP over trees; "
+                         f"host has {os.cpu_count()} logical CPUs"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32+i32", "data": "synthetic",
+            "config": {"workload": desc, "envs_per_gpu": B, "envs_total": B * world, "simulations": S, "max_nodes": N,
+                       "branching_factor": F, "embedding_bytes": E, "weighted": weighted, "discount": discount,
+                       "l2": "not flushed" if args.no_flush else "flushed between steps (512 MiB fill, outside the per-step events)",
+                       "graph": not args.no_graph, "levels_per_sim": levels_per_sim,
+                       "step": "one self-play move of all envs: root eval, set_root, S x (select, leaf, expand+backprop), "
+                               "root action, env step, re-root"},
+            "clocks": clocks,
+            "gpu_launches": int(launches_per_move * K),
+            "launches_per_step": int(launches_per_move),
+        }
+        if roofline:
+            line["roofline"] = roofline
+        if e2e:
+            line["e2e"] = e2e
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

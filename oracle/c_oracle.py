@@ -3,6 +3,7 @@ out exactly like the device trees (include/tz_abi.h).  Never imported by the pro
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
 
@@ -34,6 +35,7 @@ def lib() -> C.CDLL:
             "tzo_selfplay": [_P(TzTree), _P(TzSearchCfg), _P(TzSynthGame), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int,
                              _vp, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int],
             "tzo_num_threads": [],
+            "tzo_math": [C.c_int, _vp, C.c_float, _vp, C.c_int],
         }
         for name, args in sig.items():
             fn = getattr(_lib, name)
@@ -224,3 +226,11 @@ def selfplay(t: HostTrees, cfg: TzSearchCfg, g: TzSynthGame, num_iterations, mov
 
 def num_threads() -> int:
     return lib().tzo_num_threads()
+
+
+def math(which: str, x: np.ndarray, y: float = 1.0) -> np.ndarray:
+    """tz_expf / tz_logf / tz_powf of include/tz_math.h as compiled by gcc."""
+    x = np.ascontiguousarray(x, dtype=np.float32)
+    out = np.empty_like(x)
+    _ok(lib().tzo_math({"exp": 0, "log": 1, "pow": 2}[which], _ptr(x), y, _ptr(out), x.size), "math")
+    return out

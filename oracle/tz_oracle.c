@@ -27,6 +27,7 @@
 
 #define EXPORT __attribute__((visibility("default")))
 #define MAXF 1024
+#define PAR_MIN 64 /* below this many trees a parallel region costs more than it saves */
 
 /* ---- canonical float sum (32 strided partials + xor butterfly), see oracle/mcts_numpy.py canon_sum ---- */
 static float canon_sum(const float* x, int n) {
@@ -364,7 +365,7 @@ static void reroot(View* v, int action, int do_reset, int32_t* label /*N*/, int3
 /* exported host-memory mirror of the device C-ABI                                                    */
 /* ------------------------------------------------------------------------------------------------ */
 EXPORT int tzo_tree_init(const TzTree* t) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (t->B >= PAR_MIN)
   for (int b = 0; b < t->B; ++b) {
     View v = view(t, b);
     clear_rows(&v, 0, v.N);
@@ -374,7 +375,7 @@ EXPORT int tzo_tree_init(const TzTree* t) {
 }
 
 EXPORT int tzo_set_root(const TzTree* t, const float* root_policy, const float* root_value, void* const* root_emb) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (t->B >= PAR_MIN)
   for (int b = 0; b < t->B; ++b) {
     View v = view(t, b);
     set_root(&v, root_policy + (size_t)b * t->F, root_value[b], root_emb, b);
@@ -384,7 +385,7 @@ EXPORT int tzo_set_root(const TzTree* t, const float* root_policy, const float* 
 
 EXPORT int tzo_select(const TzTree* t, const TzSearchCfg* cfg, const TzWork* w) {
   if (t->F > MAXF) return TZ_ENOTSUP;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (t->B >= PAR_MIN)
   for (int b = 0; b < t->B; ++b) {
     View v = view(t, b);
     int parent, action, levels;
@@ -403,7 +404,7 @@ EXPORT int tzo_select(const TzTree* t, const TzSearchCfg* cfg, const TzWork* w) 
 
 EXPORT int tzo_expand_backprop(const TzTree* t, const TzSearchCfg* cfg, const TzWork* w) {
   if (t->F > MAXF) return TZ_ENOTSUP;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (t->B >= PAR_MIN)
   for (int b = 0; b < t->B; ++b) {
     View v = view(t, b);
     int parent = w->parent[b], action = w->action[b];
@@ -421,7 +422,7 @@ EXPORT int tzo_root_action(const TzTree* t, float temperature, const float* nois
                            int32_t* visits, float* policy_weights, float* root_q, int32_t* action) {
   if (t->F > MAXF) return TZ_ENOTSUP;
   int bad = 0;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (t->B >= PAR_MIN)
   for (int b = 0; b < t->B; ++b) {
     View v = view(t, b);
     size_t F = (size_t)t->F;
@@ -437,7 +438,7 @@ EXPORT int tzo_root_action(const TzTree* t, float temperature, const float* nois
 }
 
 EXPORT int tzo_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag, int persist_tree) {
-#pragma omp parallel
+#pragma omp parallel if (t->B >= PAR_MIN)
   {
     int32_t* label = (int32_t*)malloc(sizeof(int32_t) * (size_t)t->N * 2);
     int32_t* trans = label + t->N;
@@ -508,7 +509,7 @@ static void synth_leaf_one(const TzSynthGame* g, const int32_t* pcore, int actio
 }
 
 EXPORT int tzo_synth_init_states(const TzSynthGame* g, int B, int env_offset, const int32_t* episode, int32_t* core, uint8_t* payload) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (B >= PAR_MIN)
   for (int b = 0; b < B; ++b)
     synth_write_state(g, tz_synth_init_h(g->seed, (uint32_t)(b + env_offset), (uint32_t)episode[b]), 0, 0,
                       core + 4 * (size_t)b, payload ? payload + (size_t)b * g->payload_bytes : NULL);
@@ -518,7 +519,7 @@ EXPORT int tzo_synth_init_states(const TzSynthGame* g, int B, int env_offset, co
 EXPORT int tzo_synth_root(const TzSynthGame* g, int B, const int32_t* core, const float* dir_noise, float dir_eps,
                           float* root_policy, float* root_value) {
   if (g->F > MAXF) return TZ_ENOTSUP;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (B >= PAR_MIN)
   for (int b = 0; b < B; ++b)
     synth_root_one(g, core + 4 * (size_t)b, dir_noise ? dir_noise + (size_t)b * g->F : NULL, dir_eps,
                    root_policy + (size_t)b * g->F, root_value + b);
@@ -528,7 +529,7 @@ EXPORT int tzo_synth_root(const TzSynthGame* g, int B, const int32_t* core, cons
 EXPORT int tzo_synth_leaf(const TzSynthGame* g, int B, const int32_t* parent_core, const int32_t* action, float* policy,
                           float* value, uint8_t* terminated, int32_t* new_core, uint8_t* new_payload) {
   if (g->F > MAXF) return TZ_ENOTSUP;
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (B >= PAR_MIN)
   for (int b = 0; b < B; ++b)
     synth_leaf_one(g, parent_core + 4 * (size_t)b, action[b], policy + (size_t)b * g->F, value + b, terminated + b,
                    new_core + 4 * (size_t)b, new_payload ? new_payload + (size_t)b * g->payload_bytes : NULL);
@@ -551,7 +552,7 @@ static void synth_env_step_one(const TzSynthGame* g, int env, int action, int32_
 
 EXPORT int tzo_synth_env_step(const TzSynthGame* g, int B, int env_offset, const int32_t* action, int32_t* core,
                               uint8_t* payload, int32_t* episode, uint8_t* reset_flag) {
-#pragma omp parallel for schedule(static)
+#pragma omp parallel for schedule(static) if (B >= PAR_MIN)
   for (int b = 0; b < B; ++b)
     synth_env_step_one(g, b + env_offset, action[b], core + 4 * (size_t)b,
                        payload ? payload + (size_t)b * g->payload_bytes : NULL, episode + b, reset_flag + b);
@@ -630,3 +631,9 @@ EXPORT int tzo_selfplay(const TzTree* t, const TzSearchCfg* cfg, const TzSynthGa
 }
 
 EXPORT int tzo_num_threads(void) { return omp_get_max_threads(); }
+
+/* the path's own exp / log / pow (include/tz_math.h), exported so tests can pin the NumPy restatement to them */
+EXPORT int tzo_math(int which, const float* x, float y, float* out, int n) {
+  for (int i = 0; i < n; ++i) out[i] = which == 0 ? tz_expf(x[i]) : which == 1 ? tz_logf(x[i]) : tz_powf(x[i], y);
+  return 0;
+}

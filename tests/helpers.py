@@ -239,24 +239,15 @@ def tree_to_numpy(tree) -> dict:
 
 def make_cuda_evaluator(s: Schedule, game):
     import turbozero_b200 as tz
+    from turbozero_b200.synthetic import make_synthetic_evaluator
 
     sel = tz.PUCTSelector(c=s.c) if s.selector == 0 else tz.MuZeroPUCTSelector()
     base = tz.WeightedMCTS if s.weighted else tz.MCTS
-
-    class SynthRoot(base):
-        """Root evaluated by the synthetic stand-in so the policy bits equal the oracle's."""
-
-        def update_root(self, key, tree, root_embedding, params, root_metadata=None, dirichlet_noise=None, **kw):
-            pol, val = game.root_eval(root_embedding, dirichlet_noise, s.dir_eps)
-            return self._set_root(tree, pol, val, root_embedding)
-
-    kw = dict(eval_fn=None, action_selector=sel, branching_factor=game.F, max_nodes=s.N, num_iterations=s.S,
-              discount=s.discount, temperature=s.temperature, tiebreak_noise=s.tiebreak_noise, persist_tree=s.persist_tree)
+    kw = dict(action_selector=sel, max_nodes=s.N, num_iterations=s.S, discount=s.discount, temperature=s.temperature,
+              tiebreak_noise=s.tiebreak_noise, persist_tree=s.persist_tree)
     if s.weighted:
         kw["q_temperature"] = s.q_temperature
-    ev = SynthRoot(**kw)
-    ev.fma_backup = s.fma_backup
-    return ev
+    return make_synthetic_evaluator(base, game, dir_eps=s.dir_eps, fma_backup=s.fma_backup, **kw)
 
 
 def run_cuda_api(s: Schedule, fused: bool = True, snapshots: bool = False) -> Result:

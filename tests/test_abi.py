@@ -1,0 +1,107 @@
+"""The C-ABI shared libraries load without a GPU and export every symbol include/*.h declares; struct layouts seen by
+ctypes equal the C compiler's; argument validation answers before any launch.  No compute calls here."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+INCLUDE = ROOT / "include"
+
+
+@pytest.fixture(scope="module")
+def built():
+    from turbozero_b200 import build
+
+    build.build()
+    from turbozero_b200 import _abi
+
+    return _abi
+
+
+def declared_functions(header: Path):
+    text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
+    text = re.sub(r"//[^\n]*", "", text)
+    names = set()
+    for m in re.finditer(r"^\s*(?:const\s+)?(?:int|uint64_t|char\s*\*|const char\s*\*)\s+\*?\s*(tz_[a-z0-9_]+)\s*\(", text, flags=re.M):
+        names.add(m.group(1))
+    return names
+
+
+def test_headers_declare_what_ctypes_binds(built):
+    abi = declared_functions(INCLUDE / "tz_abi.h")
+    synth = declared_functions(INCLUDE / "tz_synth.h") - abi
+    assert abi == set(built.TZ_SYMBOLS), abi ^ set(built.TZ_SYMBOLS)
+    synth_exported = {n for n in synth if not n.startswith(("tz_synth_init_h", "tz_synth_step_h", "tz_synth_legal", "tz_synth_logit",
+                                                            "tz_synth_terminal", "tz_synth_reward", "tz_synth_value",
+                                                            "tz_synth_payload_word"))}
+    assert synth_exported == set(built.TZ_SYNTH_SYMBOLS), synth_exported ^ set(built.TZ_SYNTH_SYMBOLS)
+
+
+def test_libraries_export_every_declared_symbol(built):
+    lib = C.CDLL(str(built.LIB_DIR / "libtz_b200.so"))
+    for name in declared_functions(INCLUDE / "tz_abi.h"):
+        assert hasattr(lib, name), f"libtz_b200.so does not export {name}"
+    synth = C.CDLL(str(built.LIB_DIR / "libtz_synth.so"))
+    for name in built.TZ_SYNTH_SYMBOLS:
+        assert hasattr(synth, name), f"libtz_synth.so does not export {name}"
+    out = subprocess.run(["nm", "-D", "--defined-only", str(built.LIB_DIR / "libtz_b200.so")], capture_output=True, text=True).stdout
+    exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
+    assert set(built.TZ_SYMBOLS) <= exported
+
+
+def test_product_library_does_not_depend_on_oracle_or_synth(built):
+    out = subprocess.run(["ldd", str(built.LIB_DIR / "libtz_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "tz_synth" not in out
+
+
+def test_abi_version_and_strerror(built):
+    lib = built.lib()
+    assert lib.tz_abi_version() == 1
+    assert lib.tz_strerror(0) == b"ok"
+    assert b"invalid" in lib.tz_strerror(-1)
+    assert b"not supported" in lib.tz_strerror(-2)
+
+
+def test_struct_layouts_match_the_c_compiler(built, tmp_path):
+    src = tmp_path / "layout.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "tz_synth.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu\n", sizeof(TzTree), sizeof(TzSearchCfg), sizeof(TzWork), sizeof(TzSynthGame), sizeof(TzSynthCtx));
+  printf("%zu %zu %zu %zu %zu\n", offsetof(TzTree, next_free_idx), offsetof(TzTree, r), offsetof(TzTree, emb), offsetof(TzTree, emb_row_bytes), offsetof(TzTree, stats));
+  printf("%zu %zu %zu\n", offsetof(TzSearchCfg, discount), offsetof(TzSearchCfg, inv_q_temperature), offsetof(TzSearchCfg, fma_backup));
+  printf("%zu %zu %zu %zu\n", offsetof(TzWork, emb_parent), offsetof(TzWork, policy), offsetof(TzWork, emb_new), offsetof(TzWork, path));
+  return 0;
+}''')
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", f"-I{INCLUDE}", str(src), "-o", str(exe)], check=True)
+    lines = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    T, S, W = built.TzTree, built.TzSearchCfg, built.TzWork
+    assert lines[0].split() == [str(C.sizeof(x)) for x in (T, S, W, built.TzSynthGame, built.TzSynthCtx)]
+    assert lines[1].split() == [str(getattr(T, f).offset) for f in ("next_free_idx", "r", "emb", "emb_row_bytes", "stats")]
+    assert lines[2].split() == [str(getattr(S, f).offset) for f in ("discount", "inv_q_temperature", "fma_backup")]
+    assert lines[3].split() == [str(getattr(W, f).offset) for f in ("emb_parent", "policy", "emb_new", "path")]
+
+
+def test_argument_validation_needs_no_gpu(built):
+    lib = built.lib()
+    t = built.TzTree(B=0, N=4, F=3, n_emb=0)
+    assert lib.tz_tree_init(C.byref(t), None) == -1  # TZ_EINVAL: B <= 0
+    t = built.TzTree(B=1, N=4, F=3, n_emb=0)  # null array pointers
+    cfg = built.TzSearchCfg(selector=0, c=1.0, c1=0.0, c2=1.0, epsilon=1e-8, discount=-1.0)
+    w = built.TzWork()
+    assert lib.tz_select(C.byref(t), C.byref(cfg), C.byref(w), None) == -1
+    assert lib.tz_reroot(C.byref(t), None, None, 1, None) == -1
+    assert lib.tz_search(C.byref(t), C.byref(cfg), C.byref(w), 4, None, None, None) == -1  # no leaf callback
+    assert lib.tz_launch_count() == 0  # nothing was launched by any of the above
+
+
+def test_missing_library_is_a_loud_error(built, monkeypatch, tmp_path):
+    monkeypatch.setattr(built, "LIB_DIR", tmp_path)
+    with pytest.raises(built.TzError, match="no CPU or PyTorch fallback"):
+        built._load("libtz_b200.so", built.TZ_SYMBOLS)

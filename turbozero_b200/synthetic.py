@@ -176,3 +176,46 @@ class SyntheticSelfPlay:
         self.game.env_step(self.state, self.action, self.episode, self.reset_flag, self.env_offset)
         _abi.check(lib.tz_reroot(C.byref(ts), self.action.data_ptr(), self.reset_flag.data_ptr(), 1 if ev.persist_tree else 0,
                                  stream), "tz_reroot")
+
+
+def make_synthetic_evaluator(base, game: SyntheticGame, dir_eps: Optional[float] = 0.25, fma_backup: bool = False, **kwargs):
+    """An evaluator of class `base` (MCTS / WeightedMCTS) whose root evaluation is the synthetic stand-in's
+    (tz_synth_root: mcts.py:137-138, or alphazero.py:57-76 when Dirichlet noise is passed), so that root policies
+    carry the same bits as the CPU oracle's.  Everything else is the product path unchanged."""
+
+    class SyntheticRoot(base):
+        def update_root(self, key, tree, root_embedding, params, root_metadata=None, dirichlet_noise=None, **kw):
+            pol, val = game.root_eval(root_embedding, dirichlet_noise, dir_eps if dir_eps is not None else 0.0)
+            return self._set_root(tree, pol, val, root_embedding)
+
+    SyntheticRoot.__name__ = f"SyntheticRoot({base.__name__})"
+    ev = SyntheticRoot(eval_fn=None, branching_factor=game.F, **kwargs)
+    ev.fma_backup = fma_backup
+    ev.dirichlet_epsilon = dir_eps
+    return ev
+
+
+class SyntheticEnv:
+    """The synthetic game as the `env_step_fn` of core/common.py:32-103 (batched): stepping an env whose episode
+    ends re-initialises it in the same launch (common.py:95-100) and reports `terminated` for that step."""
+
+    def __init__(self, game: SyntheticGame, B: int, env_offset: int = 0, device="cuda"):
+        from .types import StepMetadata
+
+        self._md = StepMetadata
+        self.game, self.B, self.env_offset = game, B, env_offset
+        self.state, self.episode = game.init_states(B, env_offset, device=device)
+        dev = self.state["core"].device
+        self.reset_flag = torch.zeros((B,), dtype=torch.uint8, device=dev)
+        self._step = torch.zeros((B,), dtype=torch.int32, device=dev)
+        self._rewards = torch.zeros((B, 2), dtype=torch.float32, device=dev)
+        self._mask = torch.ones((B, game.F), dtype=torch.bool, device=dev)
+        self._player = torch.zeros((B,), dtype=torch.int32, device=dev)
+
+    def metadata(self):
+        return self._md(rewards=self._rewards, action_mask=self._mask, terminated=self.reset_flag, cur_player_id=self._player,
+                        step=self._step)
+
+    def env_step_fn(self, state, action: torch.Tensor):
+        self.game.env_step(state, action.to(torch.int32), self.episode, self.reset_flag, self.env_offset)
+        return state, self.metadata()
