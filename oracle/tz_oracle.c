@@ -5,11 +5,13 @@
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * oracle/_build/libtz_oracle.so.  The product library (libtz_b200.so) neither links nor calls it.
  *
- * PARITY UNPINNED upstream: the reference (lowrollr/turbozero) has no tests or golden vectors and JAX cannot be
- * installed here.  This file is pinned by hand-derived known answers and by agreement with the
- * independently written literal NumPy restatement oracle/mcts_numpy.py (different algorithms where the
- * reference allows: e.g. re-rooting here is a single forward sweep using parents[i] < i, there it is the
- * reference's N-1 label-propagation rounds + scatter).
+ * PARITY PINNING: the reference (lowrollr/turbozero) has no tests or golden vectors and JAX cannot be installed here.
+ * This file is pinned by golden fixtures produced by the reference's own unmodified source executed on a NumPy
+ * emulation of the jax API (tests/golden/, oracle/jaxshim/README.md), by hand-derived known answers
+ * and by agreement with the independently written literal NumPy restatement oracle/mcts_numpy.py (different
+ * algorithms where the reference allows: e.g. re-rooting here is a single forward sweep using parents[i] < i, there it
+ * is the reference's N-1 label-propagation rounds + scatter).  XLA's own float code generation (FMA contraction,
+ * exp/log/pow) remains unpinned -- "parity unpinned" for those bits (DESIGN.md "Residual risk").
  *
  * Host arrays use the SAME struct (TzTree/TzWork/TzSearchCfg, include/tz_abi.h) and layout as the device path.
  * Build: gcc -O2 -fopenmp -ffp-contract=off -fno-fast-math (oracle/build.py).  Reference citations are relative
