@@ -306,36 +306,28 @@ def run_native(args):
     roofline = None
     if not args.skip_roofline:
         peak, peak_src = measured_peaks()
-        moves_r = 2
-        ends = [[torch.cuda.Event(enable_timing=True) for _ in range(S)] for _ in range(moves_r)]
-        starts = [[torch.cuda.Event(enable_timing=True) for _ in range(S)] for _ in range(moves_r)]
-        cur = {"m": 0}
-        leaf_c = slib.tz_synth_leaf_cb
-        user_ptr = sp._cb[1]
-
-        def timed_leaf(user, sim, w, stream):
-            m = cur["m"]
-            ends[m][sim].record()  # closes the k_sim launch enqueued just before this callback
-            rc = leaf_c(user_ptr, sim, w, stream)
-            starts[m][sim].record()  # opens the k_sim launch enqueued right after
-            return rc
-
-        cb = _abi.LEAF_FN(timed_leaf)
+        moves_r = 3
+        if slib.tz_synth_timed_begin(S) != 0:
+            raise RuntimeError("tz_synth_timed_begin failed")
         saved = sp._cb
-        sp._cb = (C.cast(cb, C.c_void_p), user_ptr, saved[2])
+        sp._cb = (C.cast(slib.tz_synth_leaf_cb_timed, C.c_void_p), saved[1], saved[2])
+        ms_buf = (C.c_float * (S - 1))()
+        leaf_buf = (C.c_float * S)()
+        durs, leaf_durs = [], []
         st0 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
-        flush()
+        blocker = flush_buf if flush_buf is not None else torch.empty(512 << 20, dtype=torch.uint8, device=dev)
         for m in range(moves_r):
-            cur["m"] = m
             load_inputs(W + m)
+            for _ in range(24):  # ~2 ms of queued fills: the whole move is enqueued before the GPU reaches it,
+                blocker.fill_(m)  # so the events measure device time, not host enqueue gaps (and L2 starts cold)
             sp.move()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            if slib.tz_synth_timed_collect(ms_buf, leaf_buf) != 0:
+                raise RuntimeError("tz_synth_timed_collect failed")
+            durs.extend(ms_buf)  # fused launches: expand+backprop of sim s, select of sim s+1
+            leaf_durs.extend(leaf_buf)
         sp._cb = saved
         st1 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
-        durs = []
-        for m in range(moves_r):
-            for s_ in range(S - 1):  # fused launches: expand+backprop of sim s_, select of sim s_+1
-                durs.append(starts[m][s_].elapsed_time(ends[m][s_ + 1]))
         dur_ms = sum(durs) / len(durs)
         dl, ds = int(st1[0] - st0[0]), int(st1[1] - st0[1])
         bytes_total = algorithmic_bytes(dl, ds, F, E, weighted)
@@ -343,7 +335,9 @@ def run_native(args):
         achieved = bytes_per_launch / (dur_ms * 1e-3) / 1e9
         roofline = {"bound": "hbm", "kernel": "k_sim (expand+backprop of simulation i fused with select of i+1)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "algorithmic_bytes_per_launch": bytes_per_launch,
+                    "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "median_launch_us": statistics.median(durs) * 1e3,
+                    "avg_leaf_stand_in_us": sum(leaf_durs) / len(leaf_durs) * 1e3, "launches_timed": len(durs),
+                    "algorithmic_bytes_per_launch": bytes_per_launch,
                     "levels_per_sim": dl / max(ds, 1), "note": "working set (trees of 1024 envs) fits the 126 MB L2: "
                     "the kernel is L2-latency bound pointer chasing, not HBM-bandwidth bound"}
 

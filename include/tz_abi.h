@@ -29,9 +29,10 @@
 extern "C" {
 #endif
 
-#define TZ_ABI_VERSION 1
+#define TZ_ABI_VERSION 2
 #define TZ_MAX_EMB 24 /* max number of embedding pytree leaves per node */
 #define TZ_PATH_CAP 32 /* path slots kept per tree between select and backprop */
+#define TZ_PATH_STRIDE (2 * TZ_PATH_CAP + 1) /* ints per tree in TzWork.path: nodes[32], actions[32], length */
 
 #define TZ_OK 0
 #define TZ_EINVAL (-1)   /* bad argument (null pointer, B/N/F <= 0, unknown selector, ...) */
@@ -57,6 +58,11 @@ typedef struct TzTree {
   float* q;                 /* [B,N]    state.py:23 value estimate */
   float* r;                 /* [B,N] raw leaf value, weighted_mcts.py:17; NULL for plain MCTS */
   uint8_t* terminated;      /* [B,N]    state.py:24 */
+  int32_t* child_stats;     /* [B,N,F,2] DERIVED table, not part of the reference pytree: for every edge the child's
+                               {bit pattern of q[child], n[child] | terminated[child] << 31}, {0,0} where edge_map is -1
+                               -- exactly what Tree.get_child_data (tree.py:78-98) would gather.  Kept in sync by every
+                               entry point so that one selection level is ONE memory round trip; rebuild it with
+                               tz_rebuild_child_stats after writing q / n / terminated / edge_map from outside. */
   void* emb[TZ_MAX_EMB];    /* [B,N,emb_row_bytes[k]]  state.py:25, one table per pytree leaf */
   int64_t emb_row_bytes[TZ_MAX_EMB];
   uint64_t* stats;          /* optional [B,4] counters {select levels, simulations, rows before
@@ -89,8 +95,9 @@ typedef struct TzWork {
   uint8_t* terminated;      /* [B]   in: metadata.terminated (mcts.py:172,179-180) */
   void* emb_new[TZ_MAX_EMB];/* [B,row_k] in: new_embedding (mcts.py:165) */
   float* backprop_noise;    /* [B,F] in, weighted q_temperature==0 only: uniform(0,tiebreak_noise) (weighted_mcts.py:123); else NULL */
-  int32_t* path;            /* [B,TZ_PATH_CAP+1] scratch owned by the library between select and the
-                               following expand_backprop of the same trees; NULL = walk parents[] */
+  int32_t* path;            /* [B,TZ_PATH_STRIDE] scratch owned by the library between select and the following
+                               expand_backprop of the same trees (visited nodes, actions taken, path length);
+                               NULL = walk parents[] and search edge rows instead */
 } TzWork;
 
 int tz_abi_version(void);
@@ -98,6 +105,9 @@ const char* tz_strerror(int code);
 
 /* Tree.reset / init_tree over the whole allocation: core/trees/tree.py:272-298. Writes every row. */
 int tz_tree_init(const TzTree* t, tz_stream_t stream);
+
+/* Recomputes TzTree.child_stats from edge_map / q / n / terminated (one pass over [B,N,F]). */
+int tz_rebuild_child_stats(const TzTree* t, tz_stream_t stream);
 
 /* MCTS.update_root_node + Tree.set_root: mcts.py:363-384 (weighted_mcts.py:66-87), tree.py:135-150.
  * root_policy [B,F], root_value [B], root_emb[k] [B,row_k]. */

@@ -83,6 +83,12 @@ typedef struct TzSynthCtx {
 } TzSynthCtx;
 int tz_synth_leaf_cb(void* user, int sim, const TzWork* w, tz_stream_t stream);
 
+/* Bench instrumentation: a tz_leaf_fn like tz_synth_leaf_cb that also records CUDA events on the launching stream
+ * around every search launch (tz_synth_timed_begin(S) first, tz_synth_timed_collect after a sync). */
+int tz_synth_timed_begin(int n_sims);
+int tz_synth_leaf_cb_timed(void* user, int sim, const TzWork* w, tz_stream_t stream);
+int tz_synth_timed_collect(float* ms_out, float* leaf_ms_out);
+
 uint64_t tz_synth_launch_count(void);
 
 #ifdef __cplusplus

@@ -37,13 +37,16 @@ def run(name, B, S, N, weighted=False, moves=8, warm=3, graph=True, use_path=Tru
           f"{B*S/ms*1e3:.3e} sims/s, {ms*1e3/S:.2f} us/sim, levels/sim={st[0]/max(st[1],1):.2f}, nfi_mean={st[2]/moves/B:.1f} kept={st[3]/moves/B:.1f}", flush=True)
 
 if __name__ == "__main__":
-    run("connect_four", 1024, 128, 256)
-    run("connect_four", 1024, 128, 256, graph=False)
-    run("connect_four", 1024, 128, 256, use_path=False)
-    run("tic_tac_toe", 32, 64, 128)
-    run("othello", 2048, 200, 400, weighted=True, moves=4)
-    run("othello", 512, 200, 400, weighted=True, moves=4)
-    run("go_9x9", 1024, 800, 1600, moves=2, warm=1)
-    run("2048", 2048, 100, 200)
-    run("connect_four", 8192, 128, 256, moves=4)
-    run("connect_four", 65536, 128, 256, moves=2, warm=1)
+    import sys as _s
+    if len(_s.argv) > 1 and _s.argv[1] == "sweep":
+        for B in (128, 1024, 4096, 16384):
+            run("connect_four", B, 128, 256, moves=4)
+        run("tic_tac_toe", 32, 64, 128)
+    else:
+        run("connect_four", 1024, 128, 256)
+        run("connect_four", 1024, 128, 256, graph=False)
+        run("tic_tac_toe", 32, 64, 128)
+        run("othello", 512, 200, 400, weighted=True, moves=4)
+        run("go_9x9", 1024, 800, 1600, moves=2, warm=1)
+        run("2048", 2048, 100, 200)
+        run("connect_four", 65536, 128, 256, moves=2, warm=1)

@@ -19,9 +19,8 @@ def pytest_collection_modifyitems(config, items):
         has_gpu = torch.cuda.is_available()
     except Exception:
         has_gpu = False
-    if has_gpu:
-        return
-    skip = pytest.mark.skip(reason="no CUDA device")
     for item in items:
         if "gpu" in item.keywords:
-            item.add_marker(skip)
+            item.add_marker(pytest.mark.timeout(180, method="thread"))  # a wedged kernel must fail the test, not hang the box
+            if not has_gpu:
+                item.add_marker(pytest.mark.skip(reason="no CUDA device"))

@@ -237,6 +237,13 @@ def tree_to_numpy(tree) -> dict:
     return out
 
 
+def assert_child_stats_consistent(tree, what=""):
+    """The derived child_stats table the kernels maintain incrementally equals a from-scratch rebuild."""
+    kept = tree.child_stats.clone()
+    tree.rebuild_child_stats()
+    assert torch.equal(kept, tree.child_stats), f"{what}: child_stats drifted from edge_map / q / n / terminated"
+
+
 def make_cuda_evaluator(s: Schedule, game):
     import turbozero_b200 as tz
     from turbozero_b200.synthetic import make_synthetic_evaluator
@@ -282,8 +289,10 @@ def run_cuda_api(s: Schedule, fused: bool = True, snapshots: bool = False) -> Re
         actions[m], pw[m] = act.cpu().numpy(), pwm.cpu().numpy()
         if snapshots:
             snaps.append(tree_to_numpy(tree))
+        assert_child_stats_consistent(tree, f"after the search of move {m}")
         game.env_step(state, act, episode, reset_flag, s.env_offset)
         ev.step(tree, act, reset_mask=reset_flag)
+        assert_child_stats_consistent(tree, f"after re-rooting for move {m}")
     res = Result(tree_to_numpy(tree), actions, pw, snaps)
     res.stats = tree.stats.cpu().numpy().astype(np.uint64)
     return res
@@ -321,6 +330,7 @@ def run_cuda_selfplay(s: Schedule, use_path: bool = True, graph: bool = False) -
         else:
             sp.move()
         actions[m], pw[m] = sp.action.cpu().numpy(), sp.policy_weights.cpu().numpy()
+    assert_child_stats_consistent(sp.tree, "after self-play")
     res = Result(tree_to_numpy(sp.tree), actions, pw)
     res.stats = sp.tree.stats.cpu().numpy().astype(np.uint64)
     return res

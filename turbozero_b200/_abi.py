@@ -9,6 +9,8 @@ from pathlib import Path
 
 TZ_MAX_EMB = 24
 TZ_PATH_CAP = 32
+TZ_PATH_STRIDE = 2 * TZ_PATH_CAP + 1
+TZ_ABI_VERSION = 2
 TZ_SEL_PUCT = 0
 TZ_SEL_MUZERO_PUCT = 1
 
@@ -20,7 +22,7 @@ class TzTree(C.Structure):
         ("B", C.c_int32), ("N", C.c_int32), ("F", C.c_int32), ("n_emb", C.c_int32),
         ("next_free_idx", C.c_void_p), ("parents", C.c_void_p), ("edge_map", C.c_void_p),
         ("n", C.c_void_p), ("p", C.c_void_p), ("q", C.c_void_p), ("r", C.c_void_p),
-        ("terminated", C.c_void_p),
+        ("terminated", C.c_void_p), ("child_stats", C.c_void_p),
         ("emb", C.c_void_p * TZ_MAX_EMB),
         ("emb_row_bytes", C.c_int64 * TZ_MAX_EMB),
         ("stats", C.c_void_p),
@@ -67,6 +69,7 @@ TZ_SYMBOLS = {
     "tz_strerror": (C.c_char_p, [C.c_int]),
     "tz_launch_count": (C.c_uint64, []),
     "tz_tree_init": (C.c_int, [_P(TzTree), _vp]),
+    "tz_rebuild_child_stats": (C.c_int, [_P(TzTree), _vp]),
     "tz_set_root": (C.c_int, [_P(TzTree), _vp, _vp, _P(_vp), _vp]),
     "tz_select": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), _vp]),
     "tz_expand_backprop": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), _vp]),
@@ -83,6 +86,9 @@ TZ_SYNTH_SYMBOLS = {
     "tz_synth_leaf": (C.c_int, [_P(TzSynthGame), C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tz_synth_env_step": (C.c_int, [_P(TzSynthGame), C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tz_synth_leaf_cb": (C.c_int, [_vp, C.c_int, _P(TzWork), _vp]),
+    "tz_synth_timed_begin": (C.c_int, [C.c_int]),
+    "tz_synth_leaf_cb_timed": (C.c_int, [_vp, C.c_int, _P(TzWork), _vp]),
+    "tz_synth_timed_collect": (C.c_int, [_vp, _vp]),
 }
 
 
@@ -113,7 +119,7 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         _lib = _load("libtz_b200.so", TZ_SYMBOLS)
-        if _lib.tz_abi_version() != 1:
+        if _lib.tz_abi_version() != TZ_ABI_VERSION:
             raise TzError("libtz_b200.so ABI version mismatch")
     return _lib
 

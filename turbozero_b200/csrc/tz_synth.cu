@@ -227,4 +227,50 @@ int tz_synth_leaf_cb(void* user, int sim, const TzWork* w, tz_stream_t stream) {
                        ctx->game.payload_bytes > 0 ? reinterpret_cast<uint8_t*>(w->emb_new[1]) : nullptr, stream);
 }
 
+// ---- bench instrumentation: CUDA events recorded on the launching stream around every search-kernel launch ----------
+// tz_search calls the leaf callback between two search launches, so an event recorded at callback entry closes the
+// previous search launch and one recorded before returning opens the next.  Everything is enqueued from C, so the
+// caller can queue a whole move behind a blocker and read pure device-side durations afterwards.
+static cudaEvent_t* g_ev_open = nullptr;
+static cudaEvent_t* g_ev_close = nullptr;
+static int g_ev_n = 0;
+
+int tz_synth_timed_begin(int n_sims) {
+  if (n_sims <= 0) return TZ_EINVAL;
+  if (g_ev_n != n_sims) {
+    for (int i = 0; i < g_ev_n; ++i) {
+      cudaEventDestroy(g_ev_open[i]);
+      cudaEventDestroy(g_ev_close[i]);
+    }
+    delete[] g_ev_open;
+    delete[] g_ev_close;
+    g_ev_open = new cudaEvent_t[n_sims];
+    g_ev_close = new cudaEvent_t[n_sims];
+    g_ev_n = n_sims;
+    for (int i = 0; i < n_sims; ++i) {
+      if (cudaEventCreate(&g_ev_open[i]) != cudaSuccess || cudaEventCreate(&g_ev_close[i]) != cudaSuccess) return TZ_EINVAL;
+    }
+  }
+  return TZ_OK;
+}
+
+int tz_synth_leaf_cb_timed(void* user, int sim, const TzWork* w, tz_stream_t stream) {
+  if (sim < 0 || sim >= g_ev_n) return TZ_EINVAL;
+  cudaEventRecord(g_ev_close[sim], (cudaStream_t)stream);
+  const int rc = tz_synth_leaf_cb(user, sim, w, stream);
+  cudaEventRecord(g_ev_open[sim], (cudaStream_t)stream);
+  return rc;
+}
+
+// ms_out[s] = duration of the search launch between leaf s and leaf s+1 (s = 0 .. n_sims-2): the fused
+// expand+backprop(s) / select(s+1) launch.  leaf_ms_out[s] (optional) = duration of leaf s.  Call after a stream sync.
+int tz_synth_timed_collect(float* ms_out, float* leaf_ms_out) {
+  for (int s = 0; s + 1 < g_ev_n; ++s)
+    if (cudaEventElapsedTime(&ms_out[s], g_ev_open[s], g_ev_close[s + 1]) != cudaSuccess) return TZ_EINVAL;
+  if (leaf_ms_out)
+    for (int s = 0; s < g_ev_n; ++s)
+      if (cudaEventElapsedTime(&leaf_ms_out[s], g_ev_close[s], g_ev_open[s]) != cudaSuccess) return TZ_EINVAL;
+  return TZ_OK;
+}
+
 }  // extern "C"

@@ -52,7 +52,7 @@ class _Scratch:
         dev, B = tree.device, tree.batch_size
         self.parent = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.action = torch.zeros((B,), dtype=torch.int32, device=dev)
-        self.path = torch.zeros((B, _abi.TZ_PATH_CAP + 1), dtype=torch.int32, device=dev)
+        self.path = torch.zeros((B, _abi.TZ_PATH_STRIDE), dtype=torch.int32, device=dev)
         self.emb_parent = [torch.zeros((B, *shape), dtype=dt, device=dev) for shape, dt in tree.emb_leaf_shapes()]
         self.emb_parent_tree = tree.unflatten_embedding(self.emb_parent)
         self.select_only = self.work()

@@ -136,7 +136,7 @@ class SyntheticSelfPlay:
         # TzWork with static leaf buffers
         self.w_parent = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.w_action = torch.zeros((B,), dtype=torch.int32, device=dev)
-        self.w_path = torch.zeros((B, _abi.TZ_PATH_CAP + 1), dtype=torch.int32, device=dev) if use_path else None
+        self.w_path = torch.zeros((B, _abi.TZ_PATH_STRIDE), dtype=torch.int32, device=dev) if use_path else None
         self.w_policy = torch.empty((B, F), dtype=f32, device=dev)
         self.w_value = torch.empty((B,), dtype=f32, device=dev)
         self.w_term = torch.empty((B,), dtype=torch.uint8, device=dev)

@@ -52,6 +52,7 @@ class Tree:
     edge_map: torch.Tensor
     data: MCTSNode
     stats: Optional[torch.Tensor] = None  # (B,4) int64 counters, see include/tz_abi.h
+    child_stats: Optional[torch.Tensor] = None  # (B,N,F,2) int32 derived table (include/tz_abi.h TzTree.child_stats)
     _emb_leaves: List[torch.Tensor] = field(default_factory=list, repr=False)
     _emb_spec: Any = field(default=None, repr=False)
     _struct: Any = field(default=None, repr=False)
@@ -103,7 +104,10 @@ class Tree:
     def struct(self) -> _abi.TzTree:
         if self._struct is None:
             d = self.data
-            for t in (self.next_free_idx, self.parents, self.edge_map, d.n, d.p, d.q, d.terminated, *self._emb_leaves):
+            if self.child_stats is None:
+                raise _abi.TzError("tree has no child_stats table: build trees with init_tree / Evaluator.init_batched")
+            for t in (self.next_free_idx, self.parents, self.edge_map, d.n, d.p, d.q, d.terminated, self.child_stats,
+                      *self._emb_leaves):
                 assert t.is_cuda and t.is_contiguous(), "tree leaves must be contiguous CUDA tensors"
             assert self.parents.dtype == torch.int32 and self.edge_map.dtype == torch.int32 and d.n.dtype == torch.int32
             assert d.p.dtype == torch.float32 and d.q.dtype == torch.float32 and d.terminated.element_size() == 1
@@ -116,6 +120,7 @@ class Tree:
             s.n, s.p, s.q = d.n.data_ptr(), d.p.data_ptr(), d.q.data_ptr()
             s.r = d.r.data_ptr() if d.r is not None else None
             s.terminated = d.terminated.data_ptr()
+            s.child_stats = self.child_stats.data_ptr()
             for k, leaf in enumerate(self._emb_leaves):
                 s.emb[k] = leaf.data_ptr()
                 s.emb_row_bytes[k] = leaf[0, 0].numel() * leaf.element_size()
@@ -144,13 +149,20 @@ class Tree:
                                         _stream_ptr()), "tz_reroot")
         return self
 
+    def rebuild_child_stats(self) -> "Tree":
+        """Recomputes the derived child_stats table from edge_map / q / n / terminated (needed only after those
+        leaves were written from outside the kernels)."""
+        _abi.check(_abi.lib().tz_rebuild_child_stats(C.byref(self.struct()), _stream_ptr()), "tz_rebuild_child_stats")
+        return self
+
     def clone(self) -> "Tree":
         d = self.data
         leaves = [l.clone() for l in self._emb_leaves]
         nd = MCTSNode(n=d.n.clone(), p=d.p.clone(), q=d.q.clone(), terminated=d.terminated.clone(),
                       embedding=pytree.tree_unflatten(leaves, self._emb_spec), r=None if d.r is None else d.r.clone())
         return Tree(self.next_free_idx.clone(), self.parents.clone(), self.edge_map.clone(), nd,
-                    None if self.stats is None else self.stats.clone(), leaves, self._emb_spec)
+                    None if self.stats is None else self.stats.clone(),
+                    None if self.child_stats is None else self.child_stats.clone(), leaves, self._emb_spec)
 
 
 MCTSTree = Tree  # state.py:34
@@ -180,5 +192,6 @@ def init_tree(batch_size: int, max_nodes: int, branching_factor: int, template_e
         edge_map=torch.full((B, N, F), NULL_INDEX, dtype=torch.int32, device=dev),
         data=node,
         stats=torch.zeros((B, 4), dtype=torch.int64, device=dev) if stats else None,
+        child_stats=torch.zeros((B, N, F, 2), dtype=torch.int32, device=dev),
         _emb_leaves=leaves, _emb_spec=spec,
     )
