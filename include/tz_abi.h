@@ -154,6 +154,10 @@ typedef int (*tz_leaf_fn)(void* user, int sim, const TzWork* w, tz_stream_t stre
 int tz_search(const TzTree* t, const TzSearchCfg* cfg, const TzWork* w, int num_iterations,
               tz_leaf_fn leaf, void* user, tz_stream_t stream);
 
+/* Self-test: compares the kernels' straight-line division sequence with the hardware's IEEE division (div.rn) on n
+ * pseudo-random operand pairs; adds the number of differing results to *mismatches_dev (device uint64, caller-zeroed). */
+int tz_selftest_div(uint64_t n, uint32_t seed, uint64_t* mismatches_dev, tz_stream_t stream);
+
 /* Number of kernels this library has launched since load (for bench accounting). */
 uint64_t tz_launch_count(void);
 

@@ -1,0 +1,58 @@
+"""Diagnostic: per-phase clock64 stamps of k_sim for tree 0 (needs libtz_b200_prof.so built with -DTZ_PROFILE)."""
+import ctypes as C, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from turbozero_b200 import _abi
+_orig = _abi._load
+def _load(name, symbols):
+    return _orig("libtz_b200_prof.so" if name == "libtz_b200.so" else name, symbols)
+_abi._load = _load
+import turbozero_b200 as tz
+from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
+
+def run(name, B, S, N, weighted=False):
+    game = SyntheticGame.named(name, 1234)
+    ev = make_synthetic_evaluator(tz.WeightedMCTS if weighted else tz.MCTS, game, action_selector=tz.PUCTSelector(), max_nodes=N, num_iterations=S)
+    sp = SyntheticSelfPlay(game, ev, B)
+    sp.dir_noise.copy_(torch.distributions.Dirichlet(torch.full((B, game.F), 0.3)).sample().cuda())
+    sp.uniform01.uniform_()
+    lib = _abi.lib()
+    lib.tz_debug_prof.argtypes = [C.c_void_p]
+    for _ in range(3): sp.move()
+    torch.cuda.synchronize()
+    # one more move, sim by sim, reading the stamps after every fused launch
+    ts = sp.tree.struct()
+    sp.game.root_eval(sp.state, sp.dir_noise, sp.dir_eps, out=(sp.root_policy, sp.root_value))
+    ptrs = (C.c_void_p * 2)(sp.state["core"].data_ptr(), SyntheticGame._pay(sp.state))
+    st = torch.cuda.current_stream().cuda_stream
+    lib.tz_set_root(C.byref(ts), sp.root_policy.data_ptr(), sp.root_value.data_ptr(), ptrs, st)
+    lib.tz_select(C.byref(ts), C.byref(sp.cfg), C.byref(sp.work), st)
+    buf = (C.c_longlong * 64)()
+    rows = []
+    fn, user, _ = sp._cb
+    leaf = _abi.synth_lib().tz_synth_leaf_cb
+    for s in range(S - 1):
+        leaf(user, s, C.byref(sp.work), st)
+        lib.tz_expand_backprop_select(C.byref(ts), C.byref(sp.cfg), C.byref(sp.work), st)
+        torch.cuda.synchronize()
+        lib.tz_debug_prof(buf)
+        v = list(buf)
+        rows.append(v)
+    import statistics
+    def med(f): return statistics.median(f(v) for v in rows[S // 2:])
+    print(f"{name} B={B}: medians over the second half of the search (cycles)")
+    print("  total            ", med(lambda v: v[6] - v[0]))
+    print("  entry->trip2     ", med(lambda v: v[1] - v[0]))
+    print("  expand           ", med(lambda v: v[2] - v[1]))
+    print("  backprop+sync    ", med(lambda v: v[3] - v[2]))
+    print("  to select start  ", med(lambda v: v[4] - v[3]))
+    print("  select loop      ", med(lambda v: v[5] - v[4]), " levels", med(lambda v: v[7]))
+    print("  epilogue (emb)   ", med(lambda v: v[6] - v[5]))
+    print("  level 2 split: bounds(2 redux) / scores(div) / argmax(2 redux) / shuffles:",
+          med(lambda v: v[41] - v[40]), med(lambda v: v[42] - v[41]), med(lambda v: v[43] - v[42]), med(lambda v: v[44] - v[43]))
+    v = rows[-1]
+    L = int(v[7])
+    print("  last sim, per level: compute / row load:", [(v[8 + 2 * i] - (v[7 + 2 * i] if i else v[4]), (v[9 + 2 * i] - v[8 + 2 * i]) if i + 1 < L else None) for i in range(min(L, 8))])
+
+if __name__ == "__main__":
+    run("connect_four", 1024, 128, 256)

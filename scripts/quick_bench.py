@@ -5,12 +5,12 @@ import torch
 import turbozero_b200 as tz
 from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay
 
-def run(name, B, S, N, weighted=False, moves=8, warm=3, graph=True, use_path=True):
+def run(name, B, S, N, weighted=False, moves=8, warm=3, graph=True, use_path=True, pipelines=1):
     game = SyntheticGame.named(name, 1234)
     base = tz.WeightedMCTS if weighted else tz.MCTS
     kw = dict(eval_fn=None, action_selector=tz.PUCTSelector(), branching_factor=game.F, max_nodes=N, num_iterations=S)
     ev = base(**kw)
-    sp = SyntheticSelfPlay(game, ev, B, dirichlet=True, use_path=use_path)
+    sp = SyntheticSelfPlay(game, ev, B, dirichlet=True, use_path=use_path, pipelines=pipelines)
     sp.dir_noise.copy_(torch.distributions.Dirichlet(torch.full((B, game.F), 0.3)).sample().cuda())
     sp.uniform01.uniform_()
     if graph:
@@ -33,12 +33,19 @@ def run(name, B, S, N, weighted=False, moves=8, warm=3, graph=True, use_path=Tru
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / moves
     st = (sp.tree.stats.sum(0) - st0).tolist()
-    print(f"{name} B={B} S={S} N={N} weighted={weighted} graph={graph} path={use_path}: {ms:.3f} ms/move, "
+    print(f"{name} B={B} S={S} N={N} weighted={weighted} graph={graph} K={pipelines}: {ms:.3f} ms/move, "
           f"{B*S/ms*1e3:.3e} sims/s, {ms*1e3/S:.2f} us/sim, levels/sim={st[0]/max(st[1],1):.2f}, nfi_mean={st[2]/moves/B:.1f} kept={st[3]/moves/B:.1f}", flush=True)
 
 if __name__ == "__main__":
     import sys as _s
-    if len(_s.argv) > 1 and _s.argv[1] == "sweep":
+    if len(_s.argv) > 1 and _s.argv[1] == "pipe":
+        for K in (1, 2, 4, 8, 16, 32):
+            run("connect_four", 1024, 128, 256, moves=8, pipelines=K)
+        for K in (1, 4, 16):
+            run("othello", 512, 200, 400, weighted=True, moves=4, pipelines=K)
+        for K in (1, 4, 16):
+            run("go_9x9", 1024, 800, 1600, moves=2, warm=1, pipelines=K)
+    elif len(_s.argv) > 1 and _s.argv[1] == "sweep":
         for B in (128, 1024, 4096, 16384):
             run("connect_four", B, 128, 256, moves=4)
         run("tic_tac_toe", 32, 64, 128)

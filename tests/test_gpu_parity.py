@@ -78,6 +78,19 @@ def test_graph_replay_vs_oracle(name):
     _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), name)
 
 
+@pytest.mark.parametrize("name", ["ttt_cfg1", "c4", "othello_weighted", "go_muzero"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_stream_pipelined_slices_vs_oracle(name, graph):
+    """The env batch split into 3 uneven slices searched concurrently on 3 streams gives the same trees."""
+    s = Schedule(**CASES[name])
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=graph, pipelines=3), name)
+
+
+def test_connect_four_full_size_pipelined():
+    s = Schedule(game=SN.make_game("connect_four", 2001), B=1024, N=256, S=128, moves=3, temperature=1.0)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True, pipelines=8), "connect_four full, 8 pipelines")
+
+
 def test_connect_four_full_size():
     """BASELINE.json configs[1] at full size: 1024 envs x 128 simulations, N = 256, subtree persistence on."""
     s = Schedule(game=SN.make_game("connect_four", 2000), B=1024, N=256, S=128, moves=4, temperature=1.0)
@@ -85,3 +98,14 @@ def test_connect_four_full_size():
     got = run_cuda_selfplay(s, graph=True)
     _compare(ref, got, "connect_four full")
     check_invariants({k: v[:64] for k, v in got.arrays.items()})
+
+
+def test_division_sequence_is_ieee_exact():
+    """The select kernel's straight-line division (div_core) equals div.rn bit-for-bit on 2^30 operand pairs."""
+    import torch
+    from turbozero_b200 import _abi
+
+    bad = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for seed in (1, 2):
+        _abi.check(_abi.lib().tz_selftest_div(1 << 29, seed, bad.data_ptr(), torch.cuda.current_stream().cuda_stream), "selftest")
+    assert int(bad.item()) == 0

@@ -76,6 +76,7 @@ TZ_SYMBOLS = {
     "tz_expand_backprop_select": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), _vp]),
     "tz_root_action": (C.c_int, [_P(TzTree), C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tz_reroot": (C.c_int, [_P(TzTree), _vp, _vp, C.c_int, _vp]),
+    "tz_selftest_div": (C.c_int, [C.c_uint64, C.c_uint32, _vp, _vp]),
     "tz_search": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), C.c_int, _vp, _vp, _vp]),
 }
 

@@ -111,14 +111,58 @@ class SyntheticGame:
         return fn, C.cast(C.pointer(ctx), C.c_void_p), ctx
 
 
+class _SelfPlayLane:
+    """Envs [b0, b1) of a SyntheticSelfPlay: views into its buffers plus the structs the C-ABI takes."""
+
+    def __init__(self, sp: "SyntheticSelfPlay", b0: int, b1: int, stream: Optional[torch.cuda.Stream]):
+        self.sp, self.b0, self.b1, self.stream = sp, b0, b1, stream
+        sl = slice(b0, b1)
+        self.tree = sp.tree if (b0 == 0 and b1 == sp.B) else sp.tree.slice(b0, b1)
+        self.state = {k: v[sl] for k, v in sp.state.items()}
+        self.episode, self.reset_flag = sp.episode[sl], sp.reset_flag[sl]
+        self.root_policy, self.root_value = sp.root_policy[sl], sp.root_value[sl]
+        self.dir_noise = None if sp.dir_noise is None else sp.dir_noise[sl]
+        self.root_noise, self.uniform01 = sp.root_noise[sl], sp.uniform01[sl]
+        self.action, self.policy_weights = sp.action[sl], sp.policy_weights[sl]
+        w = _abi.TzWork()
+        w.parent, w.action = sp.w_parent[sl].data_ptr(), sp.w_action[sl].data_ptr()
+        w.path = sp.w_path[sl].data_ptr() if sp.w_path is not None else None
+        w.policy, w.value, w.terminated = sp.w_policy[sl].data_ptr(), sp.w_value[sl].data_ptr(), sp.w_term[sl].data_ptr()
+        for k in range(len(sp.w_emb_parent)):
+            w.emb_parent[k] = sp.w_emb_parent[k][sl].data_ptr()
+            w.emb_new[k] = sp.w_emb_new[k][sl].data_ptr()
+        self.work = w
+        self.cb = sp.game.leaf_callback(b1 - b0)
+        self.done = torch.cuda.Event() if stream is not None else None
+
+    def move(self) -> None:
+        sp = self.sp
+        lib, ev, game, stream = _abi.lib(), sp.ev, sp.game, _stream_ptr()
+        ts = self.tree.struct()
+        game.root_eval(self.state, self.dir_noise, sp.dir_eps, out=(self.root_policy, self.root_value))
+        ptrs = (C.c_void_p * 2)(self.state["core"].data_ptr(), SyntheticGame._pay(self.state))
+        _abi.check(lib.tz_set_root(C.byref(ts), self.root_policy.data_ptr(), self.root_value.data_ptr(), ptrs, stream), "tz_set_root")
+        fn, user, _keep = self.cb
+        _abi.check(lib.tz_search(C.byref(ts), C.byref(sp.cfg), C.byref(self.work), ev.num_iterations, fn, user, stream), "tz_search")
+        _abi.check(lib.tz_root_action(C.byref(ts), float(ev.temperature), self.root_noise.data_ptr(), self.uniform01.data_ptr(),
+                                      None, self.policy_weights.data_ptr(), None, self.action.data_ptr(), stream), "tz_root_action")
+        game.env_step(self.state, self.action, self.episode, self.reset_flag, sp.env_offset + self.b0)
+        _abi.check(lib.tz_reroot(C.byref(ts), self.action.data_ptr(), self.reset_flag.data_ptr(), 1 if ev.persist_tree else 0,
+                                 stream), "tz_reroot")
+
+
 class SyntheticSelfPlay:
     """Self-play of B synthetic games through the C-ABI only (no per-simulation Python): per move
     tz_synth_root -> tz_set_root -> tz_search(tz_synth_leaf_cb) -> tz_root_action -> tz_synth_env_step -> tz_reroot.
     This is `step_env_and_evaluator` (core/common.py:32-103) with the user's functions replaced by the stand-in.
-    All buffers are static, so one move is capturable in a CUDA graph."""
+    All buffers are static, so one move is capturable in a CUDA graph.
+
+    `pipelines = K > 1` splits the env batch into K contiguous slices whose moves run CONCURRENTLY on K streams
+    (fork / join around the move): trees never interact, and at ~1 K trees one dependent chain of small launches
+    leaves most of a B200 idle, so independent chains overlap almost for free.  Results are identical per tree."""
 
     def __init__(self, game: SyntheticGame, evaluator, B: int, *, env_offset: int = 0, dirichlet: bool = True,
-                 device="cuda", stats: bool = True, use_path: bool = True):
+                 device="cuda", stats: bool = True, use_path: bool = True, pipelines: int = 1):
         self.game, self.ev, self.B, self.env_offset = game, evaluator, B, env_offset
         self.dev = torch.device(device)
         self.tree: Tree = evaluator.init_batched(B, game.template_embedding(), device=device, stats=stats)
@@ -146,36 +190,40 @@ class SyntheticSelfPlay:
             leaves.append(torch.empty((B, game.payload_bytes), dtype=torch.uint8, device=dev))
             leaves2.append(torch.empty((B, game.payload_bytes), dtype=torch.uint8, device=dev))
         self.w_emb_parent, self.w_emb_new = leaves, leaves2
-        w = _abi.TzWork()
-        w.parent, w.action = self.w_parent.data_ptr(), self.w_action.data_ptr()
-        w.path = self.w_path.data_ptr() if use_path else None
-        w.policy, w.value, w.terminated = self.w_policy.data_ptr(), self.w_value.data_ptr(), self.w_term.data_ptr()
-        for k in range(len(leaves)):
-            w.emb_parent[k] = leaves[k].data_ptr()
-            w.emb_new[k] = leaves2[k].data_ptr()
-        self.work = w
         self.cfg = evaluator._cfg()
-        self._cb = game.leaf_callback(B)
         self.dir_eps = getattr(evaluator, "dirichlet_epsilon", 0.25)
+        K = max(1, min(int(pipelines), B))
+        bounds = [(k * B) // K for k in range(K + 1)]
+        self.lanes = [_SelfPlayLane(self, bounds[k], bounds[k + 1], torch.cuda.Stream(device=dev) if K > 1 else None)
+                      for k in range(K)]
+        self._fork = torch.cuda.Event() if K > 1 else None
+        # single-lane aliases kept for callers that drive the C-ABI themselves
+        self.work, self._cb = self.lanes[0].work, self.lanes[0].cb
+
+    @property
+    def pipelines(self) -> int:
+        return len(self.lanes)
 
     def launches_per_move(self) -> int:
         S = self.ev.num_iterations
-        return 1 + 1 + (1 + S + S) + 1 + 1 + 1  # root, set_root, select + S leaf + S expand, root_action, env_step, reroot
+        # root, set_root, select + S leaf + S expand, root_action, env_step, reroot -- per lane
+        return len(self.lanes) * (1 + 1 + (1 + S + S) + 1 + 1 + 1)
 
     def move(self) -> None:
         """One self-play move for all B games; enqueues only (no sync)."""
-        lib, ev, stream = _abi.lib(), self.ev, _stream_ptr()
-        ts = self.tree.struct()
-        self.game.root_eval(self.state, self.dir_noise, self.dir_eps, out=(self.root_policy, self.root_value))
-        ptrs = (C.c_void_p * 2)(self.state["core"].data_ptr(), SyntheticGame._pay(self.state))
-        _abi.check(lib.tz_set_root(C.byref(ts), self.root_policy.data_ptr(), self.root_value.data_ptr(), ptrs, stream), "tz_set_root")
-        fn, user, _keep = self._cb
-        _abi.check(lib.tz_search(C.byref(ts), C.byref(self.cfg), C.byref(self.work), ev.num_iterations, fn, user, stream), "tz_search")
-        _abi.check(lib.tz_root_action(C.byref(ts), float(ev.temperature), self.root_noise.data_ptr(), self.uniform01.data_ptr(),
-                                      None, self.policy_weights.data_ptr(), None, self.action.data_ptr(), stream), "tz_root_action")
-        self.game.env_step(self.state, self.action, self.episode, self.reset_flag, self.env_offset)
-        _abi.check(lib.tz_reroot(C.byref(ts), self.action.data_ptr(), self.reset_flag.data_ptr(), 1 if ev.persist_tree else 0,
-                                 stream), "tz_reroot")
+        if len(self.lanes) == 1:
+            self.lanes[0].cb = self._cb  # honours a caller-installed leaf callback (bench instrumentation)
+            self.lanes[0].move()
+            return
+        main = torch.cuda.current_stream()
+        self._fork.record(main)
+        for lane in self.lanes:
+            with torch.cuda.stream(lane.stream):
+                lane.stream.wait_event(self._fork)
+                lane.move()
+                lane.done.record(lane.stream)
+        for lane in self.lanes:
+            main.wait_event(lane.done)
 
 
 def make_synthetic_evaluator(base, game: SyntheticGame, dir_eps: Optional[float] = 0.25, fma_backup: bool = False, **kwargs):

@@ -155,6 +155,18 @@ class Tree:
         _abi.check(_abi.lib().tz_rebuild_child_stats(C.byref(self.struct()), _stream_ptr()), "tz_rebuild_child_stats")
         return self
 
+    def slice(self, start: int, stop: int) -> "Tree":
+        """Trees [start, stop) of this batch as a batch of their own, sharing memory (every leaf is batch-major, so a
+        contiguous range of trees is itself a dense tree batch).  Independent slices can be searched concurrently on
+        different CUDA streams -- the trees never interact."""
+        d = self.data
+        sl = lambda x: None if x is None else x[start:stop]
+        leaves = [l[start:stop] for l in self._emb_leaves]
+        nd = MCTSNode(n=d.n[start:stop], p=d.p[start:stop], q=d.q[start:stop], terminated=d.terminated[start:stop],
+                      embedding=pytree.tree_unflatten(leaves, self._emb_spec), r=sl(d.r))
+        return Tree(self.next_free_idx[start:stop], self.parents[start:stop], self.edge_map[start:stop], nd, sl(self.stats),
+                    sl(self.child_stats), leaves, self._emb_spec)
+
     def clone(self) -> "Tree":
         d = self.data
         leaves = [l.clone() for l in self._emb_leaves]
