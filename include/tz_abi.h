@@ -29,10 +29,11 @@
 extern "C" {
 #endif
 
-#define TZ_ABI_VERSION 2
+#define TZ_ABI_VERSION 3
 #define TZ_MAX_EMB 24 /* max number of embedding pytree leaves per node */
 #define TZ_PATH_CAP 32 /* path slots kept per tree between select and backprop */
-#define TZ_PATH_STRIDE (2 * TZ_PATH_CAP + 1) /* ints per tree in TzWork.path: nodes[32], actions[32], length */
+#define TZ_PATH_STRIDE (2 * TZ_PATH_CAP + 2) /* ints per tree in TzWork.path: nodes[32], actions[32], length, end child */
+#define TZ_SEL_STATE_WORDS 8 /* ints per tree in TzTree.sel_state */
 
 #define TZ_OK 0
 #define TZ_EINVAL (-1)   /* bad argument (null pointer, B/N/F <= 0, unknown selector, ...) */
@@ -63,6 +64,15 @@ typedef struct TzTree {
                                -- exactly what Tree.get_child_data (tree.py:78-98) would gather.  Kept in sync by every
                                entry point so that one selection level is ONE memory round trip; rebuild it with
                                tz_rebuild_child_stats after writing q / n / terminated / edge_map from outside. */
+  int32_t* best;            /* [B,N,2] DERIVED table: the selector's decision at every node, {action, next}, computed when
+                               the node's statistics last changed (backprop / expansion) instead of when the walk arrives:
+                               `next` >= 0 is the child the walk continues into, -1 means "no edge: expand here",
+                               -(2+c) means "child c exists and is terminal: re-expand it" (mcts.py:208-213).
+                               action == -1 marks the entry unknown (the walk then scores the node itself and fills it
+                               in).  With it MCTS.traverse is one dependent load per level.  Maintained by every entry
+                               point; reset by tz_tree_init / tz_rebuild_child_stats. */
+  int32_t* sel_state;       /* [B,TZ_SEL_STATE_WORDS] the selector parameters {selector, c, c1, c2, epsilon, discount}
+                               `best` was computed with; a launch with different parameters drops the tree's entries. */
   void* emb[TZ_MAX_EMB];    /* [B,N,emb_row_bytes[k]]  state.py:25, one table per pytree leaf */
   int64_t emb_row_bytes[TZ_MAX_EMB];
   uint64_t* stats;          /* optional [B,4] counters {select levels, simulations, rows before
@@ -106,7 +116,8 @@ const char* tz_strerror(int code);
 /* Tree.reset / init_tree over the whole allocation: core/trees/tree.py:272-298. Writes every row. */
 int tz_tree_init(const TzTree* t, tz_stream_t stream);
 
-/* Recomputes TzTree.child_stats from edge_map / q / n / terminated (one pass over [B,N,F]). */
+/* Recomputes TzTree.child_stats from edge_map / q / n / terminated (one pass over [B,N,F]) and marks every
+ * TzTree.best entry unknown. */
 int tz_rebuild_child_stats(const TzTree* t, tz_stream_t stream);
 
 /* MCTS.update_root_node + Tree.set_root: mcts.py:363-384 (weighted_mcts.py:66-87), tree.py:135-150.
@@ -157,6 +168,11 @@ int tz_search(const TzTree* t, const TzSearchCfg* cfg, const TzWork* w, int num_
 /* Self-test: compares the kernels' straight-line division sequence with the hardware's IEEE division (div.rn) on n
  * pseudo-random operand pairs; adds the number of differing results to *mismatches_dev (device uint64, caller-zeroed). */
 int tz_selftest_div(uint64_t n, uint32_t seed, uint64_t* mismatches_dev, tz_stream_t stream);
+
+/* Self-test: re-evaluates the selector at every allocated node whose TzTree.best entry is known and compares;
+ * out_dev[0] += number of wrong entries (or non-null entries past next_free_idx), out_dev[1] += entries checked
+ * (device uint64[2], caller-zeroed).  `cfg` must be the configuration the tree was last searched with. */
+int tz_selftest_best(const TzTree* t, const TzSearchCfg* cfg, uint64_t* out_dev, tz_stream_t stream);
 
 /* Number of kernels this library has launched since load (for bench accounting). */
 uint64_t tz_launch_count(void);

@@ -28,6 +28,10 @@ def run(name, B, S, N, weighted=False):
     lib.tz_set_root(C.byref(ts), sp.root_policy.data_ptr(), sp.root_value.data_ptr(), ptrs, st)
     lib.tz_select(C.byref(ts), C.byref(sp.cfg), C.byref(sp.work), st)
     buf = (C.c_longlong * 64)()
+    nw = min(B, 4096)
+    wbuf = (C.c_longlong * (4 * nw))()
+    lib.tz_debug_prof_warps.argtypes = [C.c_void_p, C.c_int]
+    spans, worst = [], []
     rows = []
     fn, user, _ = sp._cb
     leaf = _abi.synth_lib().tz_synth_leaf_cb
@@ -38,21 +42,27 @@ def run(name, B, S, N, weighted=False):
         lib.tz_debug_prof(buf)
         v = list(buf)
         rows.append(v)
+        lib.tz_debug_prof_warps(wbuf, nw)
+        w = [wbuf[4 * i:4 * i + 4] for i in range(nw)]
+        t0 = min(x[0] for x in w); t1 = max(x[1] for x in w)
+        durs = sorted(((x[1] - x[0]), x[2], x[3], x[0] - t0) for x in w)
+        spans.append((t1 - t0, durs[len(durs) // 2][0], durs[-1], max(x[0] for x in w) - t0, max(x[2] for x in w), max(x[3] for x in w)))
     import statistics
     def med(f): return statistics.median(f(v) for v in rows[S // 2:])
-    print(f"{name} B={B}: medians over the second half of the search (cycles)")
-    print("  total            ", med(lambda v: v[6] - v[0]))
-    print("  entry->trip2     ", med(lambda v: v[1] - v[0]))
-    print("  expand           ", med(lambda v: v[2] - v[1]))
-    print("  backprop+sync    ", med(lambda v: v[3] - v[2]))
-    print("  to select start  ", med(lambda v: v[4] - v[3]))
-    print("  select loop      ", med(lambda v: v[5] - v[4]), " levels", med(lambda v: v[7]))
-    print("  epilogue (emb)   ", med(lambda v: v[6] - v[5]))
-    print("  level 2 split: bounds(2 redux) / scores(div) / argmax(2 redux) / shuffles:",
-          med(lambda v: v[41] - v[40]), med(lambda v: v[42] - v[41]), med(lambda v: v[43] - v[42]), med(lambda v: v[44] - v[43]))
-    v = rows[-1]
-    L = int(v[7])
-    print("  last sim, per level: compute / row load:", [(v[8 + 2 * i] - (v[7 + 2 * i] if i else v[4]), (v[9 + 2 * i] - v[8 + 2 * i]) if i + 1 < L else None) for i in range(min(L, 8))])
+    print(f"{name} B={B}: kernel span (first warp entry -> last warp exit, ns) / median warp / slowest warp (ns, old L, new L, start offset) / last warp start offset / max old L / max new L")
+    for sp_ in spans[S // 2::max(1, S // 16)]:
+        print("   ", sp_)
+    print(f"  median span {statistics.median(x[0] for x in spans[S // 2:])} ns, median of median-warp {statistics.median(x[1] for x in spans[S // 2:])} ns")
+    print(f"{name} B={B}: medians over the second half of the search (cycles, tree 0)")
+    print("  total                      ", med(lambda v: v[6] - v[0]))
+    print("  entry -> trip 2 issued     ", med(lambda v: v[1] - v[0]))
+    print("  expand + per-level values  ", med(lambda v: v[2] - v[1]))
+    print("  path decisions (all levels)", med(lambda v: v[3] - v[2]))
+    print("  stores + emb store + sync  ", med(lambda v: v[4] - v[3]))
+    print("  walk                       ", med(lambda v: v[5] - v[4]), " levels", med(lambda v: v[7]))
+    print("  epilogue (emb gather)      ", med(lambda v: v[6] - v[5]))
 
 if __name__ == "__main__":
     run("connect_four", 1024, 128, 256)
+    run("go_9x9", 256, 400, 800)
+    run("othello", 256, 100, 200, weighted=True)

@@ -244,6 +244,23 @@ def assert_child_stats_consistent(tree, what=""):
     assert torch.equal(kept, tree.child_stats), f"{what}: child_stats drifted from edge_map / q / n / terminated"
 
 
+def assert_best_table_consistent(tree, ev, what="", expect_known=True):
+    """Every known entry of the derived best-table (the selector's cached decision per node) equals the selector
+    re-evaluated on the node's current rows; rows past next_free_idx hold the null entry."""
+    import ctypes as C
+
+    from turbozero_b200 import _abi
+
+    out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    cfg = ev._cfg()
+    _abi.check(_abi.lib().tz_selftest_best(C.byref(tree.struct()), C.byref(cfg), out.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream), "tz_selftest_best")
+    bad, known = (int(x) for x in out.tolist())
+    assert bad == 0, f"{what}: {bad} stale best-table entries (of {known} known)"
+    if expect_known:
+        assert known > 0, f"{what}: the best-table is empty"
+
+
 def make_cuda_evaluator(s: Schedule, game):
     import turbozero_b200 as tz
     from turbozero_b200.synthetic import make_synthetic_evaluator
@@ -289,9 +306,11 @@ def run_cuda_api(s: Schedule, fused: bool = True, snapshots: bool = False) -> Re
         actions[m], pw[m] = act.cpu().numpy(), pwm.cpu().numpy()
         if snapshots:
             snaps.append(tree_to_numpy(tree))
+        assert_best_table_consistent(tree, ev, f"after the search of move {m}")
         assert_child_stats_consistent(tree, f"after the search of move {m}")
         game.env_step(state, act, episode, reset_flag, s.env_offset)
         ev.step(tree, act, reset_mask=reset_flag)
+        assert_best_table_consistent(tree, ev, f"after re-rooting for move {m}", expect_known=False)
         assert_child_stats_consistent(tree, f"after re-rooting for move {m}")
     res = Result(tree_to_numpy(tree), actions, pw, snaps)
     res.stats = tree.stats.cpu().numpy().astype(np.uint64)
@@ -331,6 +350,7 @@ def run_cuda_selfplay(s: Schedule, use_path: bool = True, graph: bool = False, p
         else:
             sp.move()
         actions[m], pw[m] = sp.action.cpu().numpy(), sp.policy_weights.cpu().numpy()
+    assert_best_table_consistent(sp.tree, ev, "after self-play", expect_known=False)
     assert_child_stats_consistent(sp.tree, "after self-play")
     res = Result(tree_to_numpy(sp.tree), actions, pw)
     res.stats = sp.tree.stats.cpu().numpy().astype(np.uint64)

@@ -9,8 +9,9 @@ from pathlib import Path
 
 TZ_MAX_EMB = 24
 TZ_PATH_CAP = 32
-TZ_PATH_STRIDE = 2 * TZ_PATH_CAP + 1
-TZ_ABI_VERSION = 2
+TZ_PATH_STRIDE = 2 * TZ_PATH_CAP + 2
+TZ_SEL_STATE_WORDS = 8
+TZ_ABI_VERSION = 3
 TZ_SEL_PUCT = 0
 TZ_SEL_MUZERO_PUCT = 1
 
@@ -22,7 +23,7 @@ class TzTree(C.Structure):
         ("B", C.c_int32), ("N", C.c_int32), ("F", C.c_int32), ("n_emb", C.c_int32),
         ("next_free_idx", C.c_void_p), ("parents", C.c_void_p), ("edge_map", C.c_void_p),
         ("n", C.c_void_p), ("p", C.c_void_p), ("q", C.c_void_p), ("r", C.c_void_p),
-        ("terminated", C.c_void_p), ("child_stats", C.c_void_p),
+        ("terminated", C.c_void_p), ("child_stats", C.c_void_p), ("best", C.c_void_p), ("sel_state", C.c_void_p),
         ("emb", C.c_void_p * TZ_MAX_EMB),
         ("emb_row_bytes", C.c_int64 * TZ_MAX_EMB),
         ("stats", C.c_void_p),
@@ -77,6 +78,7 @@ TZ_SYMBOLS = {
     "tz_root_action": (C.c_int, [_P(TzTree), C.c_float, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tz_reroot": (C.c_int, [_P(TzTree), _vp, _vp, C.c_int, _vp]),
     "tz_selftest_div": (C.c_int, [C.c_uint64, C.c_uint32, _vp, _vp]),
+    "tz_selftest_best": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _vp, _vp]),
     "tz_search": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), C.c_int, _vp, _vp, _vp]),
 }
 

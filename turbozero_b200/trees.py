@@ -53,6 +53,8 @@ class Tree:
     data: MCTSNode
     stats: Optional[torch.Tensor] = None  # (B,4) int64 counters, see include/tz_abi.h
     child_stats: Optional[torch.Tensor] = None  # (B,N,F,2) int32 derived table (include/tz_abi.h TzTree.child_stats)
+    best: Optional[torch.Tensor] = None  # (B,N,2) int32 derived table: the selector's decision per node (TzTree.best)
+    sel_state: Optional[torch.Tensor] = None  # (B,8) int32 selector parameters `best` was computed with
     _emb_leaves: List[torch.Tensor] = field(default_factory=list, repr=False)
     _emb_spec: Any = field(default=None, repr=False)
     _struct: Any = field(default=None, repr=False)
@@ -104,10 +106,10 @@ class Tree:
     def struct(self) -> _abi.TzTree:
         if self._struct is None:
             d = self.data
-            if self.child_stats is None:
-                raise _abi.TzError("tree has no child_stats table: build trees with init_tree / Evaluator.init_batched")
+            if self.child_stats is None or self.best is None or self.sel_state is None:
+                raise _abi.TzError("tree has no derived tables: build trees with init_tree / Evaluator.init_batched")
             for t in (self.next_free_idx, self.parents, self.edge_map, d.n, d.p, d.q, d.terminated, self.child_stats,
-                      *self._emb_leaves):
+                      self.best, self.sel_state, *self._emb_leaves):
                 assert t.is_cuda and t.is_contiguous(), "tree leaves must be contiguous CUDA tensors"
             assert self.parents.dtype == torch.int32 and self.edge_map.dtype == torch.int32 and d.n.dtype == torch.int32
             assert d.p.dtype == torch.float32 and d.q.dtype == torch.float32 and d.terminated.element_size() == 1
@@ -121,6 +123,8 @@ class Tree:
             s.r = d.r.data_ptr() if d.r is not None else None
             s.terminated = d.terminated.data_ptr()
             s.child_stats = self.child_stats.data_ptr()
+            s.best = self.best.data_ptr()
+            s.sel_state = self.sel_state.data_ptr()
             for k, leaf in enumerate(self._emb_leaves):
                 s.emb[k] = leaf.data_ptr()
                 s.emb_row_bytes[k] = leaf[0, 0].numel() * leaf.element_size()
@@ -150,8 +154,8 @@ class Tree:
         return self
 
     def rebuild_child_stats(self) -> "Tree":
-        """Recomputes the derived child_stats table from edge_map / q / n / terminated (needed only after those
-        leaves were written from outside the kernels)."""
+        """Recomputes the derived child_stats table from edge_map / q / n / terminated and forgets the cached selector
+        decisions (needed only after those leaves were written from outside the kernels)."""
         _abi.check(_abi.lib().tz_rebuild_child_stats(C.byref(self.struct()), _stream_ptr()), "tz_rebuild_child_stats")
         return self
 
@@ -165,7 +169,7 @@ class Tree:
         nd = MCTSNode(n=d.n[start:stop], p=d.p[start:stop], q=d.q[start:stop], terminated=d.terminated[start:stop],
                       embedding=pytree.tree_unflatten(leaves, self._emb_spec), r=sl(d.r))
         return Tree(self.next_free_idx[start:stop], self.parents[start:stop], self.edge_map[start:stop], nd, sl(self.stats),
-                    sl(self.child_stats), leaves, self._emb_spec)
+                    sl(self.child_stats), sl(self.best), sl(self.sel_state), leaves, self._emb_spec)
 
     def clone(self) -> "Tree":
         d = self.data
@@ -174,7 +178,9 @@ class Tree:
                       embedding=pytree.tree_unflatten(leaves, self._emb_spec), r=None if d.r is None else d.r.clone())
         return Tree(self.next_free_idx.clone(), self.parents.clone(), self.edge_map.clone(), nd,
                     None if self.stats is None else self.stats.clone(),
-                    None if self.child_stats is None else self.child_stats.clone(), leaves, self._emb_spec)
+                    None if self.child_stats is None else self.child_stats.clone(),
+                    None if self.best is None else self.best.clone(),
+                    None if self.sel_state is None else self.sel_state.clone(), leaves, self._emb_spec)
 
 
 MCTSTree = Tree  # state.py:34
@@ -205,5 +211,7 @@ def init_tree(batch_size: int, max_nodes: int, branching_factor: int, template_e
         data=node,
         stats=torch.zeros((B, 4), dtype=torch.int64, device=dev) if stats else None,
         child_stats=torch.zeros((B, N, F, 2), dtype=torch.int32, device=dev),
+        best=torch.full((B, N, 2), -1, dtype=torch.int32, device=dev),
+        sel_state=torch.zeros((B, _abi.TZ_SEL_STATE_WORDS), dtype=torch.int32, device=dev),
         _emb_leaves=leaves, _emb_spec=spec,
     )
