@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TZ_ABI_VERSION 3
+#define TZ_ABI_VERSION 4
 #define TZ_MAX_EMB 24 /* max number of embedding pytree leaves per node */
 #define TZ_PATH_CAP 32 /* path slots kept per tree between select and backprop */
 #define TZ_PATH_STRIDE (2 * TZ_PATH_CAP + 2) /* ints per tree in TzWork.path: nodes[32], actions[32], length, end child */
@@ -59,11 +59,14 @@ typedef struct TzTree {
   float* q;                 /* [B,N]    state.py:23 value estimate */
   float* r;                 /* [B,N] raw leaf value, weighted_mcts.py:17; NULL for plain MCTS */
   uint8_t* terminated;      /* [B,N]    state.py:24 */
-  int32_t* child_stats;     /* [B,N,F,2] DERIVED table, not part of the reference pytree: for every edge the child's
-                               {bit pattern of q[child], n[child] | terminated[child] << 31}, {0,0} where edge_map is -1
-                               -- exactly what Tree.get_child_data (tree.py:78-98) would gather.  Kept in sync by every
-                               entry point so that one selection level is ONE memory round trip; rebuild it with
-                               tz_rebuild_child_stats after writing q / n / terminated / edge_map from outside. */
+  int32_t* child_stats;     /* [B,N,F,4] DERIVED table, not part of the reference pytree: for every edge one 16-byte entry
+                               {bit pattern of q[child], n[child] | terminated[child] << 31, bit pattern of p[node,a],
+                               edge_map[node,a]} with {0, 0} for the first two words where edge_map is -1 -- exactly what
+                               Tree.get_child_data (tree.py:78-98) would gather plus the node's own p and edge_map entry,
+                               so that the selector reads ONE vector per child and one selection level is ONE memory
+                               round trip.  edge_map and p stay authoritative; every entry point keeps the copies in
+                               sync (null rows are {0, 0, 0, -1}); rebuild with tz_rebuild_child_stats after writing
+                               q / n / p / terminated / edge_map from outside. */
   int32_t* best;            /* [B,N,2] DERIVED table: the selector's decision at every node, {action, next}, computed when
                                the node's statistics last changed (backprop / expansion) instead of when the walk arrives:
                                `next` >= 0 is the child the walk continues into, -1 means "no edge: expand here",
@@ -116,7 +119,7 @@ const char* tz_strerror(int code);
 /* Tree.reset / init_tree over the whole allocation: core/trees/tree.py:272-298. Writes every row. */
 int tz_tree_init(const TzTree* t, tz_stream_t stream);
 
-/* Recomputes TzTree.child_stats from edge_map / q / n / terminated (one pass over [B,N,F]) and marks every
+/* Recomputes TzTree.child_stats from edge_map / p / q / n / terminated (one pass over [B,N,F]) and marks every
  * TzTree.best entry unknown. */
 int tz_rebuild_child_stats(const TzTree* t, tz_stream_t stream);
 

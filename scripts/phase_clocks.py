@@ -55,7 +55,9 @@ def run(name, B, S, N, weighted=False):
     print(f"  median span {statistics.median(x[0] for x in spans[S // 2:])} ns, median of median-warp {statistics.median(x[1] for x in spans[S // 2:])} ns")
     print(f"{name} B={B}: medians over the second half of the search (cycles, tree 0)")
     print("  total                      ", med(lambda v: v[6] - v[0]))
-    print("  entry -> trip 2 issued     ", med(lambda v: v[1] - v[0]))
+    print("  entry -> trip 2 issued     ", med(lambda v: v[1] - v[0]), "  [trip 1 issued", med(lambda v: v[8] - v[0]),
+          " trip 1 back + selector check", med(lambda v: v[9] - v[8]), " q/n issued", med(lambda v: v[10] - v[9]),
+          " rows + table staging issued", med(lambda v: v[1] - v[10]), "]")
     print("  expand + per-level values  ", med(lambda v: v[2] - v[1]))
     print("  path decisions (all levels)", med(lambda v: v[3] - v[2]))
     print("  stores + emb store + sync  ", med(lambda v: v[4] - v[3]))

@@ -59,7 +59,7 @@ def test_product_library_does_not_depend_on_oracle_or_synth(built):
 
 def test_abi_version_and_strerror(built):
     lib = built.lib()
-    assert lib.tz_abi_version() == built.TZ_ABI_VERSION == 3
+    assert lib.tz_abi_version() == built.TZ_ABI_VERSION == 4
     assert lib.tz_strerror(0) == b"ok"
     assert b"invalid" in lib.tz_strerror(-1)
     assert b"not supported" in lib.tz_strerror(-2)

@@ -11,7 +11,7 @@ TZ_MAX_EMB = 24
 TZ_PATH_CAP = 32
 TZ_PATH_STRIDE = 2 * TZ_PATH_CAP + 2
 TZ_SEL_STATE_WORDS = 8
-TZ_ABI_VERSION = 3
+TZ_ABI_VERSION = 4
 TZ_SEL_PUCT = 0
 TZ_SEL_MUZERO_PUCT = 1
 

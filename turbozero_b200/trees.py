@@ -52,7 +52,7 @@ class Tree:
     edge_map: torch.Tensor
     data: MCTSNode
     stats: Optional[torch.Tensor] = None  # (B,4) int64 counters, see include/tz_abi.h
-    child_stats: Optional[torch.Tensor] = None  # (B,N,F,2) int32 derived table (include/tz_abi.h TzTree.child_stats)
+    child_stats: Optional[torch.Tensor] = None  # (B,N,F,4) int32 derived table (include/tz_abi.h TzTree.child_stats)
     best: Optional[torch.Tensor] = None  # (B,N,2) int32 derived table: the selector's decision per node (TzTree.best)
     sel_state: Optional[torch.Tensor] = None  # (B,8) int32 selector parameters `best` was computed with
     _emb_leaves: List[torch.Tensor] = field(default_factory=list, repr=False)
@@ -154,7 +154,7 @@ class Tree:
         return self
 
     def rebuild_child_stats(self) -> "Tree":
-        """Recomputes the derived child_stats table from edge_map / q / n / terminated and forgets the cached selector
+        """Recomputes the derived child_stats table from edge_map / p / q / n / terminated and forgets the cached selector
         decisions (needed only after those leaves were written from outside the kernels)."""
         _abi.check(_abi.lib().tz_rebuild_child_stats(C.byref(self.struct()), _stream_ptr()), "tz_rebuild_child_stats")
         return self
@@ -204,13 +204,15 @@ def init_tree(batch_size: int, max_nodes: int, branching_factor: int, template_e
         embedding=pytree.tree_unflatten(leaves, spec),
         r=torch.zeros((B, N), dtype=torch.float32, device=dev) if weighted else None,
     )
+    child_stats = torch.zeros((B, N, F, 4), dtype=torch.int32, device=dev)
+    child_stats[..., 3] = NULL_INDEX  # null entry {0, 0, 0, -1}
     return Tree(
         next_free_idx=torch.zeros((B,), dtype=torch.int32, device=dev),
         parents=torch.full((B, N), NULL_INDEX, dtype=torch.int32, device=dev),
         edge_map=torch.full((B, N, F), NULL_INDEX, dtype=torch.int32, device=dev),
         data=node,
         stats=torch.zeros((B, 4), dtype=torch.int64, device=dev) if stats else None,
-        child_stats=torch.zeros((B, N, F, 2), dtype=torch.int32, device=dev),
+        child_stats=child_stats,
         best=torch.full((B, N, 2), -1, dtype=torch.int32, device=dev),
         sel_state=torch.zeros((B, _abi.TZ_SEL_STATE_WORDS), dtype=torch.int32, device=dev),
         _emb_leaves=leaves, _emb_spec=spec,
