@@ -153,6 +153,15 @@ def cpu_selfplay_setup(wl, B, env_offset, seed):
     return CO, g, cg, cfg, t, episode, core, payload
 
 
+def host_threads(CO):
+    """All the host cores this process may use.  torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    silently make the CPU arm single-threaded: the thread count is passed to the oracle explicitly instead."""
+    try:
+        return max(len(os.sched_getaffinity(0)), 1)
+    except AttributeError:
+        return max(os.cpu_count() or 1, CO.num_threads())
+
+
 def cpu_moves(CO, cg, cfg, t, S, moves, dn, rn, u, core, payload, episode, nthreads):
     t0 = time.perf_counter()
     CO.selfplay(t, cfg, cg, S, moves, 1.0, True, 0, dn, 0.25, rn, u, core, payload, episode, nthreads)
@@ -167,7 +176,7 @@ def run_reference(args):
     name, B0, S, N, weighted, discount, desc = WORKLOADS[wl]
     B = args.envs or B0
     CO, g, cg, cfg, t, episode, core, payload = cpu_selfplay_setup(wl, B, 0, 1000)
-    threads = CO.num_threads()
+    threads = host_threads(CO)
     rng = np.random.default_rng(1)
     total = max(args.warmup, 1) + args.steps
     dn, rn, u = host_inputs(rng, total, B, g.F)
@@ -417,7 +426,7 @@ def run_native(args):
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
         CO, g, cgm, cfg, t, episode, core, payload = cpu_selfplay_setup(wl, B, 0, seed)
-        threads = CO.num_threads()
+        threads = host_threads(CO)
         dnc, rnc, uc = host_inputs(np.random.default_rng(2), 1, B, F)
         warm = 0.0
         while warm < 2.0:  # host cores of a shared box take a second or two to ramp up / schedule all threads
