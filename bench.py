@@ -45,6 +45,9 @@ METRIC = "mcts_simulations_per_sec"
 UNIT = "simulations/s"
 
 # name -> (synthetic game shape, envs per GPU, simulations, max_nodes, weighted, discount, description)
+# Programmatic dependent launches (TzSearchCfg.programmatic) are on by default except for the go_9x9 shape, whose leaf
+# stand-in runs long enough that a waiting search grid costs more than the overlap saves (profiles/r1h_pdl_modes.log).
+NO_PDL_BY_DEFAULT = {"cfg4"}
 WORKLOADS = {
     "cfg1": ("tic_tac_toe", 32, 64, 128, False, -1.0, "tic_tac_toe 32 envs x 64 sims (configs[0])"),
     "cfg2": ("connect_four", 1024, 128, 256, False, -1.0, "connect_four 1024 envs x 128 sims, persist_tree (configs[1])"),
@@ -64,6 +67,8 @@ def parse_args():
     ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-pdl", action="store_true", help="ordinary stream-ordered launches (TzSearchCfg.programmatic = 0)")
+    ap.add_argument("--pdl", action="store_true", help="force programmatic dependent launches on")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
@@ -240,9 +245,12 @@ def run_native(args):
     F, E = game.F, game.emb_bytes
     base = tz.WeightedMCTS if weighted else tz.MCTS
 
-    def new_eval():
+    use_pdl = args.pdl or (not args.no_pdl and wl not in NO_PDL_BY_DEFAULT)
+
+    def new_eval(programmatic=None):
         return make_synthetic_evaluator(base, game, action_selector=tz.PUCTSelector(), max_nodes=N, num_iterations=S,
-                                        discount=discount, temperature=1.0)
+                                        discount=discount, temperature=1.0,
+                                        programmatic=use_pdl if programmatic is None else programmatic)
 
     lib, slib = _abi.lib(), _abi.synth_lib()
 
@@ -259,56 +267,63 @@ def run_native(args):
             flush_buf.fill_(1)
 
     # ---------------- leg 1: device-resident inputs, whole move in the C-ABI (tz_search + leaf callback) ----------
-    ev = new_eval()
-    sp = SyntheticSelfPlay(game, ev, B, env_offset=rank * B, dirichlet=True, device=dev, stats=True)
     dn_d, rn_d, u_d = (torch.from_numpy(x).to(dev) for x in (dn_h, rn_h, u_h))
 
-    def load_inputs(i):
-        sp.dir_noise.copy_(dn_d[i], non_blocking=True)
-        sp.root_noise.copy_(rn_d[i], non_blocking=True)
-        sp.uniform01.copy_(u_d[i], non_blocking=True)
+    def timed_moves(programmatic, with_clocks):
+        """W warm-up + K timed self-play moves (one CUDA-graph replay each, per-step events, L2 flushed in between)."""
+        slib.tz_synth_set_programmatic(1 if programmatic else 0)
+        ev_ = new_eval(programmatic)
+        sp_ = SyntheticSelfPlay(game, ev_, B, env_offset=rank * B, dirichlet=True, device=dev, stats=True)
 
-    l0 = launches()
-    sp.move()  # un-captured first move: loads modules, sizes caches
-    torch.cuda.synchronize()
-    launches_per_move = launches() - l0
-    if args.no_graph:
-        step = sp.move
-    else:
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        cg = torch.cuda.CUDAGraph()
-        with torch.cuda.stream(side):
-            with torch.cuda.graph(cg, stream=side):
-                sp.move()
-        torch.cuda.current_stream().wait_stream(side)
-        step = cg.replay
-    for i in range(W):
-        load_inputs(i)
-        step()
-    torch.cuda.synchronize()
-    stats0 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
-    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    barrier()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(local) if rank == 0 else None
-    for i in range(K):
-        load_inputs(W + i)
-        flush()
-        evs[i][0].record()
-        step()
-        evs[i][1].record()
-    torch.cuda.synchronize()
-    barrier()
-    clocks = sampler.stop() if sampler else None
-    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
-    stats1 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
-    d_stats = stats1 - stats0
-    levels_per_sim = float(d_stats[0]) / max(float(d_stats[1]), 1.0)
-    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    max_ms = float(t_ms.item())
+        def load_inputs_(i):
+            sp_.dir_noise.copy_(dn_d[i], non_blocking=True)
+            sp_.root_noise.copy_(rn_d[i], non_blocking=True)
+            sp_.uniform01.copy_(u_d[i], non_blocking=True)
+
+        l0 = launches()
+        sp_.move()  # un-captured first move: loads modules, sizes caches
+        torch.cuda.synchronize()
+        per_move = launches() - l0
+        if args.no_graph:
+            step = sp_.move
+        else:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            cg = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(cg, stream=side):
+                    sp_.move()
+            torch.cuda.current_stream().wait_stream(side)
+            step = cg.replay
+        for i in range(W):
+            load_inputs_(i)
+            step()
+        torch.cuda.synchronize()
+        st0 = sp_.tree.stats.sum(0).cpu().numpy().astype(np.int64)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local) if (rank == 0 and with_clocks) else None
+        for i in range(K):
+            load_inputs_(W + i)
+            flush()
+            evs[i][0].record()
+            step()
+            evs[i][1].record()
+        torch.cuda.synchronize()
+        barrier()
+        clocks_ = sampler.stop() if sampler else None
+        ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
+        d_st = sp_.tree.stats.sum(0).cpu().numpy().astype(np.int64) - st0
+        t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        return float(t_ms.item()), float(d_st[0]) / max(float(d_st[1]), 1.0), per_move, clocks_, sp_, load_inputs_
+
+    other_ms = None
+    if use_pdl and not args.skip_roofline:  # the same moves with ordinary launches, for the record (config.ordinary_launches)
+        other_ms = timed_moves(False, False)[0]
+    max_ms, levels_per_sim, launches_per_move, clocks, sp, load_inputs = timed_moves(use_pdl, True)
     value = world * B * S * K / (max_ms * 1e-3)
 
     # ---------------- leg 2: roofline of the dominant kernel (k_sim), CUDA events around every launch --------------
@@ -319,6 +334,9 @@ def run_native(args):
         if slib.tz_synth_timed_begin(S) != 0:
             raise RuntimeError("tz_synth_timed_begin failed")
         saved = sp._cb
+        saved_prog = int(sp.cfg.programmatic)  # timed alone => the ordinary-launch form of the kernel (events between the
+        sp.cfg.programmatic = 0                # launches would serialise a programmatic pair anyway)
+        slib.tz_synth_set_programmatic(0)
         sp._cb = (C.cast(slib.tz_synth_leaf_cb_timed, C.c_void_p), saved[1], saved[2])
         ms_buf = (C.c_float * (S - 1))()
         leaf_buf = (C.c_float * S)()
@@ -336,13 +354,15 @@ def run_native(args):
             durs.extend(ms_buf)  # fused launches: expand+backprop of sim s, select of sim s+1
             leaf_durs.extend(leaf_buf)
         sp._cb = saved
+        sp.cfg.programmatic = saved_prog
+        slib.tz_synth_set_programmatic(1 if use_pdl else 0)
         st1 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
         dur_ms = sum(durs) / len(durs)
         dl, ds = int(st1[0] - st0[0]), int(st1[1] - st0[1])
         bytes_total = algorithmic_bytes(dl, ds, F, E, weighted)
         bytes_per_launch = bytes_total / max(ds // B, 1)
         achieved = bytes_per_launch / (dur_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": "k_sim (expand+backprop of simulation i fused with select of i+1)",
+        roofline = {"bound": "hbm", "kernel": "k_sim (expand+backprop of simulation i fused with select of i+1), ordinary-launch form, timed alone",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "median_launch_us": statistics.median(durs) * 1e3,
                     "avg_leaf_stand_in_us": sum(leaf_durs) / len(leaf_durs) * 1e3, "launches_timed": len(durs),
@@ -447,7 +467,12 @@ def run_native(args):
             "config": {"workload": desc, "envs_per_gpu": B, "envs_total": B * world, "simulations": S, "max_nodes": N,
                        "branching_factor": F, "embedding_bytes": E, "weighted": weighted, "discount": discount,
                        "l2": "not flushed" if args.no_flush else "flushed between steps (512 MiB fill, outside the per-step events)",
-                       "graph": not args.no_graph, "levels_per_sim": levels_per_sim,
+                       "graph": not args.no_graph, "programmatic_dependent_launch": use_pdl,
+                       "ordinary_launches": (None if other_ms is None else
+                                             {"value": world * B * S * K / (other_ms * 1e-3), "ms_per_step": other_ms / K,
+                                              "note": "same moves with TzSearchCfg.programmatic = 0 (the stand-in leaf kernel "
+                                                      "launched ordinarily too)"}),
+                       "levels_per_sim": levels_per_sim,
                        "step": "one self-play move of all envs: root eval, set_root, S x (select, leaf, expand+backprop), "
                                "root action, env step, re-root"},
             "clocks": clocks,

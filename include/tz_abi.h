@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TZ_ABI_VERSION 4
+#define TZ_ABI_VERSION 5
 #define TZ_MAX_EMB 24 /* max number of embedding pytree leaves per node */
 #define TZ_PATH_CAP 32 /* path slots kept per tree between select and backprop */
 #define TZ_PATH_STRIDE (2 * TZ_PATH_CAP + 2) /* ints per tree in TzWork.path: nodes[32], actions[32], length, end child */
@@ -95,6 +95,21 @@ typedef struct TzSearchCfg {
   int32_t weighted;      /* 0: MCTS.backpropagate mcts.py:231-262; 1: WeightedMCTS weighted_mcts.py:90-152 */
   float inv_q_temperature; /* float32(1/q_temperature) if q_temperature > 0, else 0 (weighted_mcts.py:113-131) */
   int32_t fma_backup;    /* 1: q update as fmaf(q, n, v) / (n+1) (XLA may contract mcts.py:322); 0: separate mul, add */
+  int32_t programmatic;  /* bit 0: the per-simulation launches (tz_expand_backprop[_select]) are PROGRAMMATIC DEPENDENT LAUNCHES
+                            (cudaLaunchAttributeProgrammaticStreamSerialization): the kernel may start while the preceding
+                            kernel in the stream is still running; it reads the TREE state and the previous select's outputs
+                            (TzWork.parent / action / path) before griddepcontrol.wait and the leaf results (TzWork.policy /
+                            value / terminated / emb_new) after it, so its launch latency and first two memory round trips
+                            overlap the user's last leaf kernel.
+                            bit 1: the kernel also executes griddepcontrol.launch_dependents once only its walk and
+                            embedding gather remain, so a following kernel that was itself launched programmatically
+                            (and waits before it reads) has its launch latency hidden too.
+                            Contract for bit 0: between two tz launches on the same trees the stream holds at least one
+                            kernel that is launched without the programmatic attribute, or that executes
+                            griddepcontrol.wait before griddepcontrol.launch_dependents (ordinary framework kernels
+                            satisfy the first form).  Pays when that kernel is short (a waiting grid is resident and takes
+                            issue slots from it): measured +12 % on configs[1] with the 2 us synthetic leaf, -7 % on the
+                            go_9x9 shape whose leaf runs 10 us (profiles/).  0: ordinary stream-ordered launches. */
 } TzSearchCfg;
 
 /* Per-simulation exchange buffers between the kernels and the host framework's

@@ -91,6 +91,10 @@ int tz_synth_timed_collect(float* ms_out, float* leaf_ms_out);
 
 uint64_t tz_synth_launch_count(void);
 
+/* 1: tz_synth_leaf launches its kernel as a programmatic dependent launch (it waits for the preceding grid before it
+ * signals its own dependents -- the form TzSearchCfg.programmatic requires of a leaf kernel).  Returns the old setting. */
+int tz_synth_set_programmatic(int on);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,26 @@ def test_stream_pipelined_slices_vs_oracle(name, graph):
     _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=graph, pipelines=3), name)
 
 
+@pytest.mark.parametrize("name", ["ttt_T0", "c4", "othello_weighted", "go_muzero", "very_deep", "no_persist", "wide_F300"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_programmatic_launch_vs_oracle(name, graph):
+    """TzSearchCfg.programmatic: per-simulation launches overlap the leaf kernel before them (tree state is read before
+    griddepcontrol.wait, leaf results after it) -- same trees, bit for bit."""
+    s = Schedule(**CASES[name], programmatic=True)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=graph), name)
+
+
+@pytest.mark.parametrize("name", ["c4", "othello_weighted_T05"])
+def test_programmatic_launch_python_loop_vs_oracle(name):
+    s = Schedule(**CASES[name], programmatic=True)
+    _compare(run_c_stepwise(s), run_cuda_api(s, fused=True), name)
+
+
+def test_connect_four_full_size_programmatic():
+    s = Schedule(game=SN.make_game("connect_four", 2002), B=1024, N=256, S=128, moves=4, temperature=1.0, programmatic=True)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), "connect_four full, programmatic launches")
+
+
 def test_connect_four_full_size_pipelined():
     s = Schedule(game=SN.make_game("connect_four", 2001), B=1024, N=256, S=128, moves=3, temperature=1.0)
     _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True, pipelines=8), "connect_four full, 8 pipelines")

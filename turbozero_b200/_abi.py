@@ -11,7 +11,7 @@ TZ_MAX_EMB = 24
 TZ_PATH_CAP = 32
 TZ_PATH_STRIDE = 2 * TZ_PATH_CAP + 2
 TZ_SEL_STATE_WORDS = 8
-TZ_ABI_VERSION = 4
+TZ_ABI_VERSION = 5
 TZ_SEL_PUCT = 0
 TZ_SEL_MUZERO_PUCT = 1
 
@@ -34,7 +34,7 @@ class TzSearchCfg(C.Structure):
     _fields_ = [
         ("selector", C.c_int32), ("c", C.c_float), ("c1", C.c_float), ("c2", C.c_float),
         ("epsilon", C.c_float), ("discount", C.c_float), ("weighted", C.c_int32),
-        ("inv_q_temperature", C.c_float), ("fma_backup", C.c_int32),
+        ("inv_q_temperature", C.c_float), ("fma_backup", C.c_int32), ("programmatic", C.c_int32),
     ]
 
 
@@ -92,6 +92,7 @@ TZ_SYNTH_SYMBOLS = {
     "tz_synth_timed_begin": (C.c_int, [C.c_int]),
     "tz_synth_leaf_cb_timed": (C.c_int, [_vp, C.c_int, _P(TzWork), _vp]),
     "tz_synth_timed_collect": (C.c_int, [_vp, _vp]),
+    "tz_synth_set_programmatic": (C.c_int, [C.c_int]),
 }
 
 

@@ -19,6 +19,7 @@ constexpr int THREADS = 64;
 constexpr int MAX_NC = 16;
 
 std::atomic<uint64_t> g_launches{0};
+std::atomic<int> g_programmatic{0};  // tz_synth_set_programmatic
 
 __device__ __forceinline__ uint32_t fkey(float x) {
   uint32_t u = __float_as_uint(x);
@@ -111,7 +112,14 @@ __global__ void __launch_bounds__(THREADS) k_root(const TzSynthGame g, const int
 __global__ void __launch_bounds__(THREADS) k_leaf(const TzSynthGame g, const int B, const int32_t* __restrict__ parent_core,
                                                 const int32_t* __restrict__ action, float* __restrict__ policy,
                                                 float* __restrict__ value, uint8_t* __restrict__ terminated, int32_t* new_core,
-                                                uint8_t* new_payload) {
+                                                uint8_t* new_payload, const int pdl) {
+  // Programmatic dependent launch, the form TzSearchCfg.programmatic asks of a leaf kernel: wait for the preceding
+  // grid (the search kernel that produced parent_core / action) FIRST, then let the next search launch be scheduled
+  // so that its tree-side prologue overlaps this kernel.
+  if (pdl) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   const int b = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const int F = g.F, nc = (F + 31) >> 5;
@@ -179,6 +187,8 @@ extern "C" {
 
 uint64_t tz_synth_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+int tz_synth_set_programmatic(int on) { return g_programmatic.exchange(on ? 1 : 0, std::memory_order_relaxed); }
+
 int tz_synth_init_states(const TzSynthGame* g, int B, int env_offset, const int32_t* episode, int32_t* core,
                          uint8_t* payload, tz_stream_t stream) {
   const int rc = check_game(g, B);
@@ -204,8 +214,22 @@ int tz_synth_leaf(const TzSynthGame* g, int B, const int32_t* parent_core, const
   if (rc) return rc;
   if (!parent_core || !action || !policy || !value || !terminated || !new_core) return TZ_EINVAL;
   if (g->payload_bytes > 0 && !new_payload) return TZ_EINVAL;
+  if (g_programmatic.load(std::memory_order_relaxed)) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3((unsigned)grid_for(B));
+    lc.blockDim = dim3(THREADS);
+    lc.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = 1;
+    const cudaError_t e = cudaLaunchKernelEx(&lc, k_leaf, *g, B, parent_core, action, policy, value, terminated, new_core, new_payload, 1);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return e == cudaSuccess ? TZ_OK : (int)e;
+  }
   k_leaf<<<grid_for(B), THREADS, 0, (cudaStream_t)stream>>>(*g, B, parent_core, action, policy, value, terminated, new_core,
-                                                          new_payload);
+                                                          new_payload, 0);
   return status();
 }
 

@@ -111,6 +111,10 @@ class MCTS(Evaluator):
         self.tiebreak_noise = tiebreak_noise
         self.persist_tree = persist_tree
         self.fma_backup = False  # see DESIGN.md "FMA": XLA may contract mcts.py:322; default is separate mul/add
+        # TzSearchCfg.programmatic: per-simulation launches overlap the tail of the leaf kernels that precede them
+        # (programmatic dependent launch).  Legal whenever `leaf_fn` / `env_step_fn` + `eval_fn` enqueue ordinary
+        # kernels (see include/tz_abi.h); off by default.
+        self.programmatic_launch = False
         action_selector.kernel_params()  # raises now if the selector has no device implementation
 
     # ------------------------------------------------------------------------------------------------
@@ -128,13 +132,18 @@ class MCTS(Evaluator):
             "persist_tree": self.persist_tree
         }
 
+    def _programmatic_bits(self) -> int:
+        """TzSearchCfg.programmatic: True -> both bits (launch programmatically and signal dependents); an int is passed on."""
+        v = self.programmatic_launch
+        return (3 if v else 0) if isinstance(v, bool) else int(v)
+
     def _cfg(self) -> _abi.TzSearchCfg:
         kp = self.action_selector.kernel_params()
         q_temp = getattr(self, "q_temperature", 1.0)
         inv_t = float(np.float32(1.0 / q_temp)) if q_temp > 0 else 0.0
         return _abi.TzSearchCfg(selector=kp["selector"], c=kp["c"], c1=kp["c1"], c2=kp["c2"], epsilon=kp["epsilon"],
                                 discount=self.discount, weighted=int(self.weighted), inv_q_temperature=inv_t,
-                                fma_backup=int(self.fma_backup))
+                                fma_backup=int(self.fma_backup), programmatic=self._programmatic_bits())
 
     # ------------------------------------------------------------------------------------------------
     def init(self, template_embedding: Any, *args, device=None, **kwargs) -> MCTSTree:  # pylint: disable=arguments-differ

@@ -226,7 +226,8 @@ class SyntheticSelfPlay:
             main.wait_event(lane.done)
 
 
-def make_synthetic_evaluator(base, game: SyntheticGame, dir_eps: Optional[float] = 0.25, fma_backup: bool = False, **kwargs):
+def make_synthetic_evaluator(base, game: SyntheticGame, dir_eps: Optional[float] = 0.25, fma_backup: bool = False,
+                             programmatic: bool = False, **kwargs):
     """An evaluator of class `base` (MCTS / WeightedMCTS) whose root evaluation is the synthetic stand-in's
     (tz_synth_root: mcts.py:137-138, or alphazero.py:57-76 when Dirichlet noise is passed), so that root policies
     carry the same bits as the CPU oracle's.  Everything else is the product path unchanged."""
@@ -239,6 +240,9 @@ def make_synthetic_evaluator(base, game: SyntheticGame, dir_eps: Optional[float]
     SyntheticRoot.__name__ = f"SyntheticRoot({base.__name__})"
     ev = SyntheticRoot(eval_fn=None, branching_factor=game.F, **kwargs)
     ev.fma_backup = fma_backup
+    ev.programmatic_launch = programmatic
+    if programmatic:  # the stand-in's leaf kernel then waits-then-signals, as TzSearchCfg.programmatic requires
+        _abi.synth_lib().tz_synth_set_programmatic(1)
     ev.dirichlet_epsilon = dir_eps
     return ev
 
