@@ -106,6 +106,20 @@ def test_connect_four_full_size_programmatic():
     _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), "connect_four full, programmatic launches")
 
 
+def test_reroot_one_table_at_a_time_fallback():
+    """Rows too wide for the all-tables staging area (large batch -> 16 KB stage, 20 KB embedding rows) take k_reroot."""
+    s = Schedule(game=G(F=3, payload_bytes=20000, rho256=230, tau1024=20, max_depth=12, seed=21), B=2100, N=6, S=5, moves=3,
+                 temperature=1.0)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s), "wide rows")
+
+
+def test_reroot_odd_row_sizes():
+    """Embedding leaves whose row size is not a multiple of 4 go through the byte path of the all-tables re-root."""
+    s = Schedule(game=G(F=6, payload_bytes=13, rho256=200, tau1024=30, max_depth=20, seed=22), B=37, N=40, S=30, moves=5,
+                 temperature=1.0)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s), "odd rows")
+
+
 def test_connect_four_full_size_pipelined():
     s = Schedule(game=SN.make_game("connect_four", 2001), B=1024, N=256, S=128, moves=3, temperature=1.0)
     _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True, pipelines=8), "connect_four full, 8 pipelines")
