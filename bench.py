@@ -354,6 +354,19 @@ def run_native(args):
             durs.extend(ms_buf)  # fused launches: expand+backprop of sim s, select of sim s+1
             leaf_durs.extend(leaf_buf)
         sp._cb = saved
+        # the re-root launch of three more moves, timed the same way (the streaming kernel of the path)
+        rr_ms, rr_st0 = [], sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
+        for m in range(moves_r):
+            load_inputs(W + m)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            sp.reroot_events = (e0, e1)
+            for _ in range(24):
+                blocker.fill_(m)
+            sp.move()
+            torch.cuda.synchronize()
+            rr_ms.append(e0.elapsed_time(e1))
+        sp.reroot_events = None
+        rr_st = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64) - rr_st0
         sp.cfg.programmatic = saved_prog
         slib.tz_synth_set_programmatic(1 if use_pdl else 0)
         st1 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
@@ -362,13 +375,30 @@ def run_native(args):
         bytes_total = algorithmic_bytes(dl, ds, F, E, weighted)
         bytes_per_launch = bytes_total / max(ds // B, 1)
         achieved = bytes_per_launch / (dur_ms * 1e-3) / 1e9
+        traffic = None
+        if wl == "cfg2" and B == B0:  # per-launch DRAM bytes of this kernel on this shape, from the committed ncu capture
+            try:
+                with open(os.path.join(ROOT, "profiles", "ksim_traffic.json")) as f:
+                    traffic = float(json.load(f)["traffic_bytes_per_launch"])
+            except Exception:
+                traffic = None
         roofline = {"bound": "hbm", "kernel": "k_sim (expand+backprop of simulation i fused with select of i+1), ordinary-launch form, timed alone",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "profiles/ksim_traffic.json (ncu --set full, cold L2)" if traffic else None,
                     "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "median_launch_us": statistics.median(durs) * 1e3,
                     "avg_leaf_stand_in_us": sum(leaf_durs) / len(leaf_durs) * 1e3, "launches_timed": len(durs),
                     "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "levels_per_sim": dl / max(ds, 1), "note": "working set (trees of 1024 envs) fits the 126 MB L2: "
-                    "the kernel is L2-latency bound pointer chasing, not HBM-bandwidth bound"}
+                    "levels_per_sim": dl / max(ds, 1), "note": "a launch moves ~2 MB for 1024 trees: it is bound by the "
+                    "dependent chain of one warp per tree (L2 / DRAM latency), not by bandwidth; see DESIGN.md section 3"}
+        # bytes_reroot = 4 nfi + 2 K R + (nfi - K) R per tree, R = 8F + 13 + E (+4 weighted)
+        R_row = 8 * F + 13 + E + (4 if weighted else 0)
+        rr_bytes = (4 * int(rr_st[2]) + R_row * (int(rr_st[3]) + int(rr_st[2]))) / moves_r
+        rr_avg_ms = sum(rr_ms) / len(rr_ms)
+        rr_achieved = rr_bytes / (rr_avg_ms * 1e-3) / 1e9
+        roofline["reroot"] = {"bound": "hbm", "kernel": "k_reroot_all (get_subtree / reset of every tree, one launch per move)",
+                              "achieved": rr_achieved, "peak": peak, "unit": "GB/s", "frac": rr_achieved / peak,
+                              "avg_launch_us": rr_avg_ms * 1e3, "algorithmic_bytes_per_launch": rr_bytes,
+                              "rows_before": int(rr_st[2]) / moves_r / B, "rows_kept": int(rr_st[3]) / moves_r / B}
 
     # ---------------- leg 3: e2e through the public Python API with host buffers -----------------------------------
     e2e = None

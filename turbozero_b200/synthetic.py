@@ -147,8 +147,13 @@ class _SelfPlayLane:
         _abi.check(lib.tz_root_action(C.byref(ts), float(ev.temperature), self.root_noise.data_ptr(), self.uniform01.data_ptr(),
                                       None, self.policy_weights.data_ptr(), None, self.action.data_ptr(), stream), "tz_root_action")
         game.env_step(self.state, self.action, self.episode, self.reset_flag, sp.env_offset + self.b0)
+        evs = sp.reroot_events  # optional (start, end) CUDA events around the re-root launch (bench instrumentation)
+        if evs is not None:
+            evs[0].record()
         _abi.check(lib.tz_reroot(C.byref(ts), self.action.data_ptr(), self.reset_flag.data_ptr(), 1 if ev.persist_tree else 0,
                                  stream), "tz_reroot")
+        if evs is not None:
+            evs[1].record()
 
 
 class SyntheticSelfPlay:
@@ -191,6 +196,7 @@ class SyntheticSelfPlay:
             leaves2.append(torch.empty((B, game.payload_bytes), dtype=torch.uint8, device=dev))
         self.w_emb_parent, self.w_emb_new = leaves, leaves2
         self.cfg = evaluator._cfg()
+        self.reroot_events = None
         self.dir_eps = getattr(evaluator, "dirichlet_epsilon", 0.25)
         K = max(1, min(int(pipelines), B))
         bounds = [(k * B) // K for k in range(K + 1)]
