@@ -208,6 +208,7 @@ class Array:
     def __mul__(self, o): return _binary(np.multiply, self, o)
     def __rmul__(self, o): return _binary(np.multiply, o, self)
     def __neg__(self): return Array(-self._v)
+    def __mod__(self, o): return _binary(np.remainder, self, o)  # jnp.remainder: sign of the divisor, like NumPy
 
     def __truediv__(self, o):
         rd = result_dtype(self, o)

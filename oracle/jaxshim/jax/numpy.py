@@ -98,7 +98,9 @@ def sqrt(x):
 
 
 def log(x):
-    return Array(_pathmath().tz_logf(np.asarray(unwrap(x), dtype=np.float32)))
+    v = np.asarray(unwrap(x), dtype=np.float32)
+    out = np.asarray(_pathmath().tz_logf(v), dtype=np.float32)
+    return Array(np.where(v == 0, np.float32(-np.inf), out).astype(np.float32))  # jnp.log(0) = -inf
 
 
 def exp(x):
@@ -115,3 +117,20 @@ def broadcast_to(x, shape):
 
 def searchsorted(a, v):
     return Array(np.searchsorted(unwrap(a), unwrap(v), side="left").astype(np.int32))
+
+
+# ---- the slice core/memory/replay_memory.py adds -----------------------------------------------------------------
+def ones(shape, dtype=None):
+    return Array(np.ones(shape, dtype=_default(dtype, np.float32)))
+
+
+def empty_like(x):  # XLA materialises `empty` as zeros
+    return Array(np.zeros_like(unwrap(x)))
+
+
+def unravel_index(indices, shape):
+    return tuple(Array(np.asarray(a).astype(np.int32)) for a in np.unravel_index(np.asarray(unwrap(indices)), shape))
+
+
+def argsort(x):
+    return Array(np.argsort(np.asarray(unwrap(x)), kind="stable").astype(np.int32))

@@ -34,6 +34,9 @@ class Tape:
     def dirichlet(self, key, alpha):
         raise NotImplementedError
 
+    def gumbel(self, key, shape):
+        raise NotImplementedError
+
 
 _tape = Tape()
 
@@ -51,8 +54,19 @@ def dirichlet(key, alpha):
     return Array(_tape.dirichlet(key, alpha), dtype=jnp.float32)
 
 
+def gumbel(key, shape=(), dtype=None):
+    return Array(_tape.gumbel(key, tuple(shape)), dtype=jnp.float32)
+
+
 def choice(key, a, shape=(), replace=True, p=None):
-    assert shape == () and p is not None
+    assert p is not None
+    if not replace:
+        # jax.random.choice without replacement (jax 0.4.35 _src/random.py): Gumbel top-k,
+        #   g = -gumbel(key, (n,)) - log(p);  ind = argsort(g)[:n_draws]
+        n = int(a)
+        g = -gumbel(key, (n,)) - jnp.log(p)
+        return jnp.argsort(g)[: int(shape[0])]
+    assert shape == ()
     p_cuml = jnp.cumsum(p)
     r = p_cuml[-1] * (1 - uniform(key, ()))
     return jnp.searchsorted(p_cuml, r)

@@ -65,3 +65,37 @@ def test_two_rank_sharded_search_equals_unsharded(tmp_path):
     nfi = np.concatenate([np.load(tmp_path / f"nfi{r}.npy") for r in range(world)])
     assert np.array_equal(nfi, ref.arrays["next_free_idx"])
     assert np.load(tmp_path / "elapsed.npy")[0] == pytest.approx(0.002)
+
+
+def _merge_worker(rank, world, port, n_per_rank, k, out_dir):
+    sys.path.insert(0, os.path.dirname(HERE))
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from turbozero_b200.common import merge_topk
+
+    scores = torch.from_numpy(np.load(os.path.join(out_dir, "scores.npy"))[rank])
+    order = torch.sort(scores, stable=True).indices[:k]  # this rank's k best, like EpisodeReplayBuffer.sample
+    owner, local = merge_topk(scores[order], order + rank * n_per_rank, k, n_per_rank)
+    if rank == 1:
+        np.save(os.path.join(out_dir, "owner.npy"), owner.numpy())
+        np.save(os.path.join(out_dir, "local.npy"), local.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_cross_rank_replay_sample_merge_equals_global_argsort(tmp_path):
+    """EpisodeReplayBuffer.sample across ranks (core/memory/replay_memory.py:157-169 samples over the device axis): the
+    winners of the per-rank candidate merge are the first k of one stable argsort over the concatenated blocks."""
+    world, n, k = 2, 40, 12
+    rng = np.random.default_rng(3)
+    scores = rng.standard_normal((world, n)).astype(np.float32)
+    scores[0, 5:20] = np.inf          # unsampleable slots
+    scores[1, 3] = scores[0, 2]       # a tie across ranks: the lower global index wins
+    scores[1, :30] = np.inf           # rank 1 has fewer than k candidates
+    scores[1, 3] = scores[0, 2]
+    np.save(tmp_path / "scores.npy", scores)
+    port = _free_port()
+    mp.spawn(_merge_worker, args=(world, port, n, k, str(tmp_path)), nprocs=world, join=True)
+    ref = np.argsort(scores.reshape(-1), kind="stable")[:k]
+    assert np.array_equal(np.load(tmp_path / "owner.npy") * n + np.load(tmp_path / "local.npy"), ref)

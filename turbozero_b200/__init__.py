@@ -2,9 +2,11 @@
 reference's own Evaluator / MCTS API.  See DESIGN.md and INTEGRATION.md."""
 from .action_selection import MCTSActionSelector, MuZeroPUCTSelector, PUCTSelector, normalize_q_values
 from .alphazero import AlphaZero
-from .common import partition, shard_slice, step_env_and_evaluator
+from .collect import CollectionState, collect
+from .common import merge_topk, partition, shard_slice, step_env_and_evaluator
 from .evaluator import EvalOutput, Evaluator
 from .mcts import MCTS, MCTSOutput, TraversalState
+from .replay_memory import BaseExperience, EpisodeReplayBuffer, ReplayBufferState
 from .trees import MCTSNode, MCTSTree, Tree, WeightedMCTSNode, init_tree
 from .types import StepMetadata
 from .weighted_mcts import WeightedMCTS
@@ -13,5 +15,6 @@ __all__ = [
     "MCTS", "WeightedMCTS", "AlphaZero", "MCTSOutput", "TraversalState", "Evaluator", "EvalOutput",
     "MCTSActionSelector", "PUCTSelector", "MuZeroPUCTSelector", "normalize_q_values",
     "Tree", "MCTSTree", "MCTSNode", "WeightedMCTSNode", "init_tree", "StepMetadata",
-    "partition", "shard_slice", "step_env_and_evaluator",
+    "partition", "shard_slice", "step_env_and_evaluator", "merge_topk",
+    "BaseExperience", "ReplayBufferState", "EpisodeReplayBuffer", "CollectionState", "collect",
 ]

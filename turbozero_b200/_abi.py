@@ -48,6 +48,17 @@ class TzWork(C.Structure):
     ]
 
 
+class TzReplay(C.Structure):
+    """include/tz_replay.h"""
+    _fields_ = [
+        ("B", C.c_int32), ("capacity", C.c_int32), ("n_leaves", C.c_int32), ("reward_leaf", C.c_int32),
+        ("reward_dim", C.c_int32), ("pad", C.c_int32),
+        ("next_idx", C.c_void_p), ("episode_start_idx", C.c_void_p), ("populated", C.c_void_p), ("has_reward", C.c_void_p),
+        ("leaf", C.c_void_p * TZ_MAX_EMB),
+        ("leaf_row_bytes", C.c_int64 * TZ_MAX_EMB),
+    ]
+
+
 class TzSynthGame(C.Structure):
     _fields_ = [
         ("F", C.c_int32), ("payload_bytes", C.c_int32), ("rho256", C.c_int32), ("tau1024", C.c_int32),
@@ -80,6 +91,12 @@ TZ_SYMBOLS = {
     "tz_selftest_div": (C.c_int, [C.c_uint64, C.c_uint32, _vp, _vp]),
     "tz_selftest_best": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _vp, _vp]),
     "tz_search": (C.c_int, [_P(TzTree), _P(TzSearchCfg), _P(TzWork), C.c_int, _vp, _vp, _vp]),
+    # include/tz_replay.h
+    "tz_replay_init": (C.c_int, [_P(TzReplay), _vp]),
+    "tz_replay_collect": (C.c_int, [_P(TzReplay), C.c_int, _P(_vp), _vp, _vp, _vp, _vp]),
+    "tz_replay_count_valid": (C.c_int, [_P(TzReplay), _vp, _vp]),
+    "tz_replay_sample_scores": (C.c_int, [_P(TzReplay), _vp, _vp, _vp, _vp]),
+    "tz_replay_gather": (C.c_int, [_P(TzReplay), _vp, C.c_int, _P(_vp), _vp]),
 }
 
 TZ_SYNTH_SYMBOLS = {

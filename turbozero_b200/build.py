@@ -28,7 +28,7 @@ NVCC_FLAGS = [
 ]
 
 TARGETS = {
-    "libtz_b200.so": ["csrc/tz_kernels.cu"],
+    "libtz_b200.so": ["csrc/tz_kernels.cu", "csrc/tz_replay.cu"],
     "libtz_synth.so": ["csrc/tz_synth.cu"],
 }
 

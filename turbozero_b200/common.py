@@ -24,6 +24,30 @@ def shard_slice(batch_size: int, rank: int, world_size: int) -> slice:
     return slice(rank * per, (rank + 1) * per)
 
 
+def merge_topk(scores: torch.Tensor, global_index: torch.Tensor, k: int, per_rank: int, group=None):
+    """Global `k` smallest of per-rank candidate lists (each rank passes its own k best, ascending, with indices offset by
+    rank * per_rank): all-gather the candidates, sort by (score, global index) -- the stable order a single argsort over the
+    concatenated blocks would give -- and return (owner rank, index inside the owner's block) of the winners.
+    Used by EpisodeReplayBuffer.sample across ranks (core/memory/replay_memory.py:157-169 samples over the device axis)."""
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+    pad = k - scores.numel()
+    if pad > 0:  # fewer than k slots on this rank
+        scores = torch.cat([scores, torch.full((pad,), float("inf"), dtype=scores.dtype, device=scores.device)])
+        global_index = torch.cat([global_index, torch.full((pad,), torch.iinfo(torch.int64).max, dtype=torch.int64,
+                                                           device=global_index.device)])
+    all_s = [torch.empty_like(scores) for _ in range(world)]
+    all_i = [torch.empty_like(global_index) for _ in range(world)]
+    dist.all_gather(all_s, scores.contiguous(), group=group)
+    dist.all_gather(all_i, global_index.contiguous(), group=group)
+    s, i = torch.cat(all_s), torch.cat(all_i)
+    by_index = torch.sort(i, stable=True).indices            # candidates in global-index order ...
+    pick = by_index[torch.sort(s[by_index], stable=True).indices[:k]]  # ... then a stable sort by score
+    win = i[pick]
+    return win // per_rank, win % per_rank
+
+
 def step_env_and_evaluator(
     key,
     env_state: Any,
