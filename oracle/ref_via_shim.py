@@ -186,3 +186,120 @@ def run_reference(s, snapshots: bool = False):
         finals.append(_tree_arrays(tree, P))
     stack = lambda lst: {k: np.stack([t[k] for t in lst]) for k in lst[0]}
     return stack(finals), actions, pw, ([stack(x) for x in snaps] if snapshots else None)
+
+
+def run_reference_two_player(g: SN.SynthGame, ev_kw_1: dict, ev_kw_2: dict, p1_first, max_steps: int, dir_noise, root_noise,
+                             uniform01, dir_alpha=0.3, dir_eps=0.25):
+    """Two AlphaZero(MCTS) evaluators playing each other, one game at a time, through the reference's own
+    `two_player_game_step` (core/common.py:146-232) driven exactly as `two_player_game` drives it (common.py:303-355: a
+    turn for each player per scan step, skipped once `completed`), with who-moves-first given per game (`p1_first[b]`,
+    the reference draws it with jax.random.randint, common.py:276).  Noise arrays are indexed [half_step, game].
+    Returns per-half-step records: action (-1 where the game was already completed), p1 / p2 value estimates, completed,
+    and the final outcomes (B, 2)."""
+    R = load_reference()
+    jax = R["jax"]
+    jnp = jax.numpy
+    StepMetadata = R["types"].StepMetadata
+    C = R["common"]
+    F, P = g.F, g.payload_bytes
+    B = len(p1_first)
+
+    def state(h, depth, player):
+        emb = g.make_emb(h, depth, player)
+        st = {"core": jnp.array(emb[0].view("<i4").copy(), dtype=jnp.int32)}
+        if P > 0:
+            st["payload"] = jnp.array(emb[1], dtype=jnp.uint8)
+        return st
+
+    def read(st):
+        c = np.asarray(st["core"]).astype(np.int64)
+        return int(c[0]) & 0xFFFFFFFF, int(c[1]), int(c[2])
+
+    def metadata(h, depth, player, terminated):
+        rew = g.reward(h)
+        return StepMetadata(rewards=jnp.array(np.array([rew, rew], np.float32)), action_mask=jnp.array(g.mask(h)),  # as the stand-in's leaf: one reward for both seats
+                            terminated=jnp.array(bool(terminated), dtype=jnp.bool_),
+                            cur_player_id=jnp.array(player, dtype=jnp.int32), step=jnp.array(depth, dtype=jnp.int32))
+
+    def eval_fn(env_state, params, key):
+        h, _, _ = read(env_state)
+        return jnp.array(g.logits(h)), jnp.array(g.value(h), dtype=jnp.float32)
+
+    def env_step_fn(env_state, action):
+        h, depth, player = read(env_state)
+        h2, d2 = g.step_h(h, int(action)), depth + 1
+        return state(h2, d2, 1 - player), metadata(h2, d2, 1 - player, g.terminal(h2, d2))
+
+    def make_ev(kw):
+        return R["alphazero"].AlphaZero(R["mcts"].MCTS)(
+            dirichlet_alpha=dir_alpha, dirichlet_epsilon=dir_eps, eval_fn=eval_fn,
+            action_selector=R["action_selection"].PUCTSelector(c=kw.get("c", 1.0)), branching_factor=F, max_nodes=kw["N"],
+            num_iterations=kw["S"], discount=-1.0, temperature=kw.get("temperature", 1.0), tiebreak_noise=1e-8, persist_tree=True)
+
+    ev1, ev2 = make_ev(ev_kw_1), make_ev(ev_kw_2)
+    BASE = 1000
+    cur = {"b": 0}
+
+    class Tape(jax.random.Tape):
+        # state.key = (BASE,) + (1,)*t at half-step t; step_key = state.key + (0,) (common.py:180); then as in run_reference:
+        # evaluate key = step_key + (1,) (common.py:71); + (0,) root sampling (mcts.py:94-103); + (1, 1) dirichlet (alphazero.py:57)
+        @staticmethod
+        def _parse(p):
+            assert p[0] == BASE
+            t = 0
+            while p[1 + t] == 1:
+                t += 1
+            assert p[1 + t] == 0
+            return t, p[2 + t:]
+
+        def uniform(self, key, shape, minval, maxval):
+            t, rest = self._parse(key.path)
+            assert rest == (1, 0), key.path
+            return uniform01[t, cur["b"]] if shape == () else root_noise[t, cur["b"]]
+
+        def dirichlet(self, key, alpha):
+            t, rest = self._parse(key.path)
+            assert rest == (1, 1, 1), key.path
+            return dir_noise[t, cur["b"]]
+
+    jax.random.install_tape(Tape())
+    T = (max_steps // 2) * 2
+    actions = np.full((T, B), -1, np.int32)
+    p1v, p2v = np.zeros((T, B), np.float32), np.zeros((T, B), np.float32)
+    completed = np.zeros((T, B), bool)
+    outcomes = np.zeros((B, 2), np.float32)
+    p1_nfi, p2_nfi = np.zeros((T, B), np.int32), np.zeros((T, B), np.int32)
+    for b in range(B):
+        cur["b"] = b
+        h0 = g.init_h(b, 0)
+        env_state, md = state(h0, 0, 0), metadata(h0, 0, 0, False)
+        st = C.TwoPlayerGameState(
+            key=jax.random.Key((BASE,)), env_state=env_state, env_state_metadata=md,
+            p1_eval_state=ev1.init(template_embedding=env_state), p2_eval_state=ev2.init(template_embedding=env_state),
+            p1_value_estimate=jnp.array(0.0, dtype=jnp.float32), p2_value_estimate=jnp.array(0.0, dtype=jnp.float32),
+            outcomes=jnp.zeros((2,), dtype=jnp.float32), completed=jnp.zeros((), dtype=jnp.bool_))
+        recorded = {}
+        orig = C.step_env_and_evaluator
+
+        def spy(**kw):  # records the action the active evaluator chose
+            out = orig(**kw)
+            recorded["action"] = int(out[0].action)
+            return out
+
+        C.step_env_and_evaluator = spy
+        try:
+            for t in range(T):
+                use_p1 = bool(p1_first[b]) == (t % 2 == 0)
+                if not bool(st.completed):  # common.py:305-317 / 327-339
+                    # the key advances only when a step is taken; keep the tape's half-step index equal to t
+                    st = st.replace(key=jax.random.Key((BASE,) + (1,) * t))
+                    st = C.two_player_game_step(st, p1_evaluator=ev1, p2_evaluator=ev2, params=None, env_step_fn=env_step_fn,
+                                                env_init_fn=None, use_p1=use_p1, max_steps=max_steps)
+                    actions[t, b] = recorded["action"]
+                p1v[t, b], p2v[t, b] = float(st.p1_value_estimate), float(st.p2_value_estimate)
+                completed[t, b] = bool(st.completed)
+                p1_nfi[t, b], p2_nfi[t, b] = int(st.p1_eval_state.next_free_idx), int(st.p2_eval_state.next_free_idx)
+        finally:
+            C.step_env_and_evaluator = orig
+        outcomes[b] = np.asarray(st.outcomes)
+    return dict(actions=actions, p1_value=p1v, p2_value=p2v, completed=completed, outcomes=outcomes, p1_nfi=p1_nfi, p2_nfi=p2_nfi)

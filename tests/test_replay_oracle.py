@@ -81,3 +81,19 @@ def test_masks_leave_other_envs_untouched():
     RN.truncate(s, np.array([True, False, False]))
     assert not s.populated[0].any() and s.populated[2, 0] and s.next_idx.tolist() == [0, 1, 1]
     assert np.array_equal(before.buffer["reward"][2], s.buffer["reward"][2])
+
+
+def test_fixtures_regenerate_from_the_reference_source():
+    """With /root/reference mounted: running the reference's replay_memory.py / common.py two_player_game_step again (on
+    oracle/jaxshim) reproduces the committed replay_*.npz and two_player_*.npz byte for byte."""
+    import subprocess
+    import sys
+
+    from oracle import ref_via_shim as RV
+
+    if not RV.available():
+        pytest.skip("/root/reference is not mounted here")
+    for script in ("make_golden_replay.py", "make_golden_two_player.py"):
+        res = subprocess.run([sys.executable, os.path.join(GOLDEN, script), "--check"], capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert res.stdout.count("matches") >= 2

@@ -3,7 +3,8 @@ reference's own Evaluator / MCTS API.  See DESIGN.md and INTEGRATION.md."""
 from .action_selection import MCTSActionSelector, MuZeroPUCTSelector, PUCTSelector, normalize_q_values
 from .alphazero import AlphaZero
 from .collect import CollectionState, collect
-from .common import merge_topk, partition, shard_slice, step_env_and_evaluator
+from .common import (GameFrame, TwoPlayerGameState, merge_topk, partition, shard_slice, step_env_and_evaluator,
+                     two_player_game, two_player_game_step)
 from .evaluator import EvalOutput, Evaluator
 from .mcts import MCTS, MCTSOutput, TraversalState
 from .replay_memory import BaseExperience, EpisodeReplayBuffer, ReplayBufferState
@@ -16,5 +17,6 @@ __all__ = [
     "MCTSActionSelector", "PUCTSelector", "MuZeroPUCTSelector", "normalize_q_values",
     "Tree", "MCTSTree", "MCTSNode", "WeightedMCTSNode", "init_tree", "StepMetadata",
     "partition", "shard_slice", "step_env_and_evaluator", "merge_topk",
+    "TwoPlayerGameState", "GameFrame", "two_player_game_step", "two_player_game",
     "BaseExperience", "ReplayBufferState", "EpisodeReplayBuffer", "CollectionState", "collect",
 ]
