@@ -173,7 +173,7 @@ def cpu_moves(CO, cg, cfg, t, S, moves, dn, rn, u, core, payload, episode, nthre
     return time.perf_counter() - t0
 
 
-def run_reference(args):
+def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -207,13 +207,13 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    out.append(json.dumps(line))
 
 
 # ------------------------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------------------------
-def run_native(args):
+def run_native(args, out):
     import torch
     import torch.distributed as dist
 
@@ -515,17 +515,30 @@ def run_native(args):
             line["e2e"] = e2e
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        out.append(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
     args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_native(args)
+    # stdout carries exactly ONE line (the JSON): libraries that print there (NCCL's version banner under torchrun) are
+    # sent to stderr for the duration of the run, and the real stdout is restored for the final print
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    out = []
+    try:
+        if args.impl == "reference":
+            run_reference(args, out)
+        else:
+            run_native(args, out)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in out:
+        print(line, flush=True)
 
 
 if __name__ == "__main__":
