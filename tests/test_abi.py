@@ -101,6 +101,36 @@ def test_argument_validation_needs_no_gpu(built):
     assert lib.tz_launch_count() == 0  # nothing was launched by any of the above
 
 
+def test_replay_argument_validation_needs_no_gpu(built):
+    """include/tz_replay.h entry points reject malformed descriptors before touching the device."""
+    lib = built.lib()
+    r = built.TzReplay(B=0, capacity=4, n_leaves=1, reward_leaf=0, reward_dim=2)
+    assert lib.tz_replay_init(C.byref(r), None) == -1  # B <= 0
+    r = built.TzReplay(B=2, capacity=4, n_leaves=1, reward_leaf=0, reward_dim=2)  # null state pointers
+    assert lib.tz_replay_collect(C.byref(r), 0, None, None, None, None, None) == -1
+    assert lib.tz_replay_count_valid(C.byref(r), None, None) == -1
+    assert lib.tz_replay_gather(C.byref(r), None, 3, None, None) == -1
+    assert C.sizeof(built.TzReplay) == 6 * 4 + 4 * 8 + built.TZ_MAX_EMB * 16
+
+
+def test_replay_struct_layout_matches_header(built, tmp_path):
+    src = tmp_path / "layout_replay.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stddef.h>
+#include "tz_replay.h"
+int main(void) {
+  printf("%zu %zu %zu %zu %zu %zu\n", sizeof(TzReplay), offsetof(TzReplay, reward_dim), offsetof(TzReplay, next_idx),
+         offsetof(TzReplay, has_reward), offsetof(TzReplay, leaf), offsetof(TzReplay, leaf_row_bytes));
+  return 0;
+}''')
+    exe = tmp_path / "layout_replay"
+    subprocess.run(["gcc", f"-I{INCLUDE}", str(src), "-o", str(exe)], check=True)
+    got = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()
+    R = built.TzReplay
+    assert got == [str(C.sizeof(R))] + [str(getattr(R, f).offset) for f in ("reward_dim", "next_idx", "has_reward", "leaf", "leaf_row_bytes")]
+
+
 def test_missing_library_is_a_loud_error(built, monkeypatch, tmp_path):
     monkeypatch.setattr(built, "LIB_DIR", tmp_path)
     with pytest.raises(built.TzError, match="no CPU or PyTorch fallback"):
