@@ -70,5 +70,25 @@ def build(force: bool = False, verbose: bool = False) -> None:
         stamp.write_text(want + "\n")
 
 
+def build_jax_ffi() -> Path:
+    """csrc/tz_jax_ffi.cc -> lib/libtz_jax_ffi.so (the XLA FFI handlers of turbozero_b200/ffi_jax.py).  Needs jax for the XLA
+    FFI headers (`jax.ffi.include_dir()`); NOT buildable in the image this repo was developed in (no jax, no network)."""
+    try:
+        try:
+            from jax import ffi as jffi
+        except ImportError:
+            from jax.extend import ffi as jffi
+    except ImportError as e:
+        raise RuntimeError("build_jax_ffi() needs jax >= 0.4.35 for the XLA FFI headers") from e
+    build()
+    out = LIB_DIR / "libtz_jax_ffi.so"
+    cmd = [_nvcc(), "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", f"-I{INCLUDE}", f"-I{jffi.include_dir()}",
+           str(PKG / "csrc" / "tz_jax_ffi.cc"), f"-L{LIB_DIR}", "-l:libtz_b200.so", f"-Xlinker=-rpath={LIB_DIR}", "-o", str(out)]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError(f"nvcc failed for libtz_jax_ffi.so:\n{res.stdout}\n{res.stderr}")
+    return out
+
+
 if __name__ == "__main__":
     build(force="--force" in sys.argv, verbose="-v" in sys.argv)
