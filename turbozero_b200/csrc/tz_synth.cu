@@ -113,17 +113,20 @@ __global__ void __launch_bounds__(THREADS) k_leaf(const TzSynthGame g, const int
                                                 const int32_t* __restrict__ action, float* __restrict__ policy,
                                                 float* __restrict__ value, uint8_t* __restrict__ terminated, int32_t* new_core,
                                                 uint8_t* new_payload, const int pdl) {
-  // Programmatic dependent launch, the form TzSearchCfg.programmatic asks of a leaf kernel: wait for the preceding
-  // grid (the search kernel that produced parent_core / action) FIRST, then let the next search launch be scheduled
-  // so that its tree-side prologue overlaps this kernel.
-  if (pdl) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-  }
   const int b = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   const int F = g.F, nc = (F + 31) >> 5;
   const int32_t* pc = parent_core + 4 * (size_t)b;
+  // Programmatic dependent launch, the form TzSearchCfg.programmatic asks of a leaf kernel: wait for the preceding
+  // grid (the search kernel that produced parent_core / action) FIRST, then let the next search launch be scheduled
+  // so that its tree-side prologue overlaps this kernel.  The parameter loads and index arithmetic above are inputs of
+  // the wait, so they happen before it.
+  if (pdl) {
+    asm volatile("griddepcontrol.wait;" ::"l"(pc), "l"(action), "l"(policy), "l"(value), "l"(terminated), "l"(new_core),
+                 "l"(new_payload), "r"(F), "r"(g.rho256), "r"(g.payload_bytes)
+                 : "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   const uint32_t h2 = tz_synth_step_h((uint32_t)pc[0], (uint32_t)action[b]);
   const int d2 = pc[1] + 1;
   const int term = tz_synth_terminal(h2, d2, g.tau1024, g.max_depth);
