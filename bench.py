@@ -86,7 +86,7 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -94,7 +94,7 @@ class ClockSampler:
         self.proc = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
 
@@ -239,7 +239,7 @@ def run_native(args, out):
     wl = args.workload
     name, B0, S, N, weighted, discount, desc = WORKLOADS[wl]
     B = args.envs or B0
-    K, W = args.steps, args.warmup
+    K, W = args.steps, max(args.warmup, 3)  # timing rule: never fewer than 3 warm-up steps
     seed = 1000 + rank
     game = SyntheticGame.named(name, seed)
     F, E = game.F, game.emb_bytes
@@ -304,6 +304,7 @@ def run_native(args, out):
         barrier()
         torch.cuda.synchronize()
         sampler = ClockSampler(local) if (rank == 0 and with_clocks) else None
+        t_wall0 = time.perf_counter()
         for i in range(K):
             load_inputs_(W + i)
             flush()
@@ -311,7 +312,15 @@ def run_native(args, out):
             step()
             evs[i][1].record()
         torch.cuda.synchronize()
+        ms_wall = time.perf_counter() - t_wall0
         barrier()
+        if sampler is not None:
+            # the timed region may be shorter than a few sampling periods: keep the SAME load running (untimed replays of the
+            # same step) until ~0.6 s of it has been sampled, so that the clocks line describes the GPU under this load
+            t_end = time.perf_counter() + max(0.0, 0.6 - ms_wall)
+            while time.perf_counter() < t_end:
+                step()
+                torch.cuda.synchronize()
         clocks_ = sampler.stop() if sampler else None
         ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
         d_st = sp_.tree.stats.sum(0).cpu().numpy().astype(np.int64) - st0
