@@ -48,6 +48,7 @@ UNIT = "simulations/s"
 # Programmatic dependent launches (TzSearchCfg.programmatic) are on by default except for the go_9x9 shape, whose leaf
 # stand-in runs long enough that a waiting search grid costs more than the overlap saves (profiles/r1h_pdl_modes.log).
 NO_PDL_BY_DEFAULT = {"cfg4"}
+REPLAY_CAPACITY = 256  # slots per env of the episode replay buffer in the cfg5 step
 WORKLOADS = {
     "cfg1": ("tic_tac_toe", 32, 64, 128, False, -1.0, "tic_tac_toe 32 envs x 64 sims (configs[0])"),
     "cfg2": ("connect_four", 1024, 128, 256, False, -1.0, "connect_four 1024 envs x 128 sims, persist_tree (configs[1])"),
@@ -246,6 +247,7 @@ def run_native(args, out):
     base = tz.WeightedMCTS if weighted else tz.MCTS
 
     use_pdl = args.pdl or (not args.no_pdl and wl not in NO_PDL_BY_DEFAULT)
+    with_replay = wl == "cfg5"  # "full self-play + replay memory" (BASELINE.json configs[4])
 
     def new_eval(programmatic=None):
         return make_synthetic_evaluator(base, game, action_selector=tz.PUCTSelector(), max_nodes=N, num_iterations=S,
@@ -280,19 +282,41 @@ def run_native(args, out):
             sp_.root_noise.copy_(rn_d[i], non_blocking=True)
             sp_.uniform01.copy_(u_d[i], non_blocking=True)
 
+        one_move = sp_.move
+        if with_replay:
+            # configs[4] names "full self-play + replay memory": the collection step's buffer update (Trainer.collect,
+            # core/training/train.py:300-340 -> tz_replay_collect) runs inside the step, fed from static buffers
+            rb = tz.EpisodeReplayBuffer(capacity=REPLAY_CAPACITY)
+            obs0 = sp_.state["core"].to(torch.float32)
+            rstate = rb.init(B, tz.BaseExperience(reward=torch.zeros((1,)), policy_weights=torch.zeros((F,)),
+                                                  policy_mask=torch.zeros((F,), dtype=torch.bool), observation_nn=obs0[0].cpu(),
+                                                  cur_player_id=torch.zeros((), dtype=torch.int32)), device=dev)
+            x_obs, x_mask = torch.empty_like(obs0), torch.ones((B, F), dtype=torch.bool, device=dev)
+            x_rew0, x_rew = torch.zeros((B, 1), device=dev), torch.empty((B, 1), device=dev)
+            x_player = torch.zeros((B,), dtype=torch.int32, device=dev)
+            x_trunc = torch.zeros((B,), dtype=torch.uint8, device=dev)
+
+            def one_move():
+                x_obs.copy_(sp_.state["core"])  # the position the search runs on (int32 -> float32 features)
+                sp_.move()
+                x_rew.copy_(sp_.reset_flag.unsqueeze(1))  # stand-in reward: 1 where the episode ended
+                exp = tz.BaseExperience(reward=x_rew0, policy_weights=sp_.policy_weights, policy_mask=x_mask,
+                                        observation_nn=x_obs, cur_player_id=x_player)
+                rb.collect_update(rstate, [exp], x_rew, sp_.reset_flag, x_trunc)
+
         l0 = launches()
-        sp_.move()  # un-captured first move: loads modules, sizes caches
+        one_move()  # un-captured first move: loads modules, sizes caches
         torch.cuda.synchronize()
         per_move = launches() - l0
         if args.no_graph:
-            step = sp_.move
+            step = one_move
         else:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             cg = torch.cuda.CUDAGraph()
             with torch.cuda.stream(side):
                 with torch.cuda.graph(cg, stream=side):
-                    sp_.move()
+                    one_move()
             torch.cuda.current_stream().wait_stream(side)
             step = cg.replay
         for i in range(W):
@@ -513,8 +537,10 @@ def run_native(args, out):
                                                       "launched ordinarily too)"}),
                        "levels_per_sim": levels_per_sim,
                        "step": "one self-play move of all envs: root eval, set_root, S x (select, leaf, expand+backprop), "
-                               "root action, env step, re-root"},
+                               "root action, env step, re-root" + (", replay-buffer update (tz_replay_collect, capacity "
+                                                                    f"{REPLAY_CAPACITY})" if with_replay else "")},
             "clocks": clocks,
+            "env_steps_per_sec": value / S,  # the metric's second half: self-play env steps of the whole job per second
             "gpu_launches": int(launches_per_move * K),
             "launches_per_step": int(launches_per_move),
         }

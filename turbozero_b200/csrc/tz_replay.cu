@@ -10,6 +10,13 @@
 #include "tz_math.h"
 #include "tz_replay.h"
 
+#include <atomic>
+
+namespace tz_internal {
+std::atomic<uint64_t> g_replay_launches{0};  // added to tz_launch_count() (tz_kernels.cu)
+uint64_t replay_launches() { return g_replay_launches.load(std::memory_order_relaxed); }
+}  // namespace tz_internal
+
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
@@ -126,7 +133,8 @@ int check_replay(const TzReplay* r) {
   return TZ_OK;
 }
 
-inline int status() {
+inline int status(int launches = 1) {
+  tz_internal::g_replay_launches.fetch_add((uint64_t)launches, std::memory_order_relaxed);
   const cudaError_t e = cudaPeekAtLastError();
   return e == cudaSuccess ? TZ_OK : (int)e;
 }
