@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TZ_ABI_VERSION 5
+#define TZ_ABI_VERSION 6
 #define TZ_MAX_EMB 24 /* max number of embedding pytree leaves per node */
 #define TZ_PATH_CAP 32 /* path slots kept per tree between select and backprop */
 #define TZ_PATH_STRIDE (2 * TZ_PATH_CAP + 2) /* ints per tree in TzWork.path: nodes[32], actions[32], length, end child */
@@ -126,6 +126,13 @@ typedef struct TzWork {
   int32_t* path;            /* [B,TZ_PATH_STRIDE] scratch owned by the library between select and the following
                                expand_backprop of the same trees (visited nodes, actions taken, path length);
                                NULL = walk parents[] and search edge rows instead */
+  int32_t* path_spill;      /* optional [B,path_spill_cap,2] scratch, same ownership: {node, action} of the path levels that
+                               no longer fit the 32-level ring of `path` (level l of a path of length L > 32 is kept here
+                               for l < L - 32).  With it a deep backup processes 32 levels per memory round trip like the
+                               ring does; without it (NULL) levels above the ring are reached by chasing parents[], one
+                               dependent round trip each.  path_spill_cap >= max_nodes - 32 covers every possible path. */
+  int32_t path_spill_cap;   /* entries per tree in path_spill */
+  int32_t pad;
 } TzWork;
 
 int tz_abi_version(void);

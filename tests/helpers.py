@@ -318,7 +318,7 @@ def run_cuda_api(s: Schedule, fused: bool = True, snapshots: bool = False) -> Re
     return res
 
 
-def run_cuda_selfplay(s: Schedule, use_path: bool = True, graph: bool = False, pipelines: int = 1) -> Result:
+def run_cuda_selfplay(s: Schedule, use_path: bool = True, graph: bool = False, pipelines: int = 1, use_spill: bool = True) -> Result:
     """The CUDA path with the whole simulation loop inside the C-ABI (tz_search + tz_synth_leaf_cb)."""
     import torch
     from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay
@@ -327,7 +327,7 @@ def run_cuda_selfplay(s: Schedule, use_path: bool = True, graph: bool = False, p
     game = SyntheticGame(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
     ev = make_cuda_evaluator(s, game)
     sp = SyntheticSelfPlay(game, ev, s.B, env_offset=s.env_offset, dirichlet=s.dirichlet, use_path=use_path,
-                           pipelines=pipelines)
+                           pipelines=pipelines, use_spill=use_spill)
     sp.dir_eps = s.dir_eps
     actions = np.zeros((s.moves, s.B), np.int32)
     pw = np.zeros((s.moves, s.B, g.F), np.float32)

@@ -106,6 +106,29 @@ def test_connect_four_full_size_programmatic():
     _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), "connect_four full, programmatic launches")
 
 
+DEEP = {
+    # paths far deeper than the 32-level ring: narrow (lane-per-level kernels) and wide (82-way, 3 register chunks) trees
+    "deep_narrow": dict(game=G(F=2, payload_bytes=4, rho256=0, tau1024=0, max_depth=1000, seed=12), B=5, N=160, S=140, moves=3,
+                        temperature=1.0, discount=0.97),
+    "deep_wide_go": dict(game=G(F=82, payload_bytes=24, rho256=1, tau1024=0, max_depth=600, seed=31), B=4, N=220, S=180, moves=3,
+                         temperature=1.0),
+    "deep_muzero_pos": dict(game=G(F=12, payload_bytes=0, rho256=2, tau1024=0, max_depth=600, seed=32), B=4, N=150, S=130, moves=3,
+                            temperature=1.0, discount=1.0, selector=1, dirichlet=False),
+}
+
+
+@pytest.mark.parametrize("name", list(DEEP))
+@pytest.mark.parametrize("use_spill", [True, False])
+@pytest.mark.parametrize("programmatic", [False, True])
+def test_deep_paths_vs_oracle(name, use_spill, programmatic):
+    """Backups through paths of 60-150 levels: with the spilled path record (deep_windows: 32 levels per round trip, decisions
+    recomputed) and without it (parents[] chase) -- same trees as the oracle either way."""
+    s = Schedule(**DEEP[name], programmatic=programmatic)
+    ref = run_c_treemajor(s)
+    assert ref.stats[:, 0].sum() / max(ref.stats[:, 1].sum(), 1) > 15, "the schedule is meant to produce deep paths"
+    _compare(ref, run_cuda_selfplay(s, use_spill=use_spill), name)
+
+
 def test_reroot_one_table_at_a_time_fallback():
     """Rows too wide for the all-tables staging area (large batch -> 16 KB stage, 20 KB embedding rows) take k_reroot."""
     s = Schedule(game=G(F=3, payload_bytes=20000, rho256=230, tau1024=20, max_depth=12, seed=21), B=2100, N=6, S=5, moves=3,

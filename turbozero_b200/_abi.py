@@ -11,7 +11,7 @@ TZ_MAX_EMB = 24
 TZ_PATH_CAP = 32
 TZ_PATH_STRIDE = 2 * TZ_PATH_CAP + 2
 TZ_SEL_STATE_WORDS = 8
-TZ_ABI_VERSION = 5
+TZ_ABI_VERSION = 6
 TZ_SEL_PUCT = 0
 TZ_SEL_MUZERO_PUCT = 1
 
@@ -45,6 +45,7 @@ class TzWork(C.Structure):
         ("policy", C.c_void_p), ("value", C.c_void_p), ("terminated", C.c_void_p),
         ("emb_new", C.c_void_p * TZ_MAX_EMB),
         ("backprop_noise", C.c_void_p), ("path", C.c_void_p),
+        ("path_spill", C.c_void_p), ("path_spill_cap", C.c_int32), ("pad", C.c_int32),
     ]
 
 

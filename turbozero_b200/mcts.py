@@ -53,6 +53,8 @@ class _Scratch:
         self.parent = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.action = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.path = torch.zeros((B, _abi.TZ_PATH_STRIDE), dtype=torch.int32, device=dev)
+        # levels of paths deeper than the 32-level ring (TzWork.path_spill): every possible path fits
+        self.path_spill = torch.zeros((B, max(tree.capacity - _abi.TZ_PATH_CAP, 1), 2), dtype=torch.int32, device=dev)
         self.emb_parent = [torch.zeros((B, *shape), dtype=dt, device=dev) for shape, dt in tree.emb_leaf_shapes()]
         self.emb_parent_tree = tree.unflatten_embedding(self.emb_parent)
         self.select_only = self.work()
@@ -61,6 +63,7 @@ class _Scratch:
              backprop_noise=None) -> _abi.TzWork:
         w = _abi.TzWork()
         w.parent, w.action, w.path = self.parent.data_ptr(), self.action.data_ptr(), self.path.data_ptr()
+        w.path_spill, w.path_spill_cap = self.path_spill.data_ptr(), int(self.path_spill.shape[1])
         for k, t in enumerate(self.emb_parent):
             w.emb_parent[k] = t.data_ptr()
         if policy is not None:

@@ -127,6 +127,8 @@ class _SelfPlayLane:
         w = _abi.TzWork()
         w.parent, w.action = sp.w_parent[sl].data_ptr(), sp.w_action[sl].data_ptr()
         w.path = sp.w_path[sl].data_ptr() if sp.w_path is not None else None
+        if sp.w_path_spill is not None:
+            w.path_spill, w.path_spill_cap = sp.w_path_spill[sl].data_ptr(), int(sp.w_path_spill.shape[1])
         w.policy, w.value, w.terminated = sp.w_policy[sl].data_ptr(), sp.w_value[sl].data_ptr(), sp.w_term[sl].data_ptr()
         for k in range(len(sp.w_emb_parent)):
             w.emb_parent[k] = sp.w_emb_parent[k][sl].data_ptr()
@@ -167,7 +169,8 @@ class SyntheticSelfPlay:
     leaves most of a B200 idle, so independent chains overlap almost for free.  Results are identical per tree."""
 
     def __init__(self, game: SyntheticGame, evaluator, B: int, *, env_offset: int = 0, dirichlet: bool = True,
-                 device="cuda", stats: bool = True, use_path: bool = True, pipelines: int = 1):
+                 device="cuda", stats: bool = True, use_path: bool = True, pipelines: int = 1,
+                 use_spill: bool = True):
         self.game, self.ev, self.B, self.env_offset = game, evaluator, B, env_offset
         self.dev = torch.device(device)
         self.tree: Tree = evaluator.init_batched(B, game.template_embedding(), device=device, stats=stats)
@@ -186,6 +189,9 @@ class SyntheticSelfPlay:
         self.w_parent = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.w_action = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.w_path = torch.zeros((B, _abi.TZ_PATH_STRIDE), dtype=torch.int32, device=dev) if use_path else None
+        N_ = evaluator.max_nodes
+        self.w_path_spill = (torch.zeros((B, max(N_ - _abi.TZ_PATH_CAP, 1), 2), dtype=torch.int32, device=dev)
+                             if (use_path and use_spill) else None)
         self.w_policy = torch.empty((B, F), dtype=f32, device=dev)
         self.w_value = torch.empty((B,), dtype=f32, device=dev)
         self.w_term = torch.empty((B,), dtype=torch.uint8, device=dev)
