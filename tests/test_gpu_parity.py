@@ -157,6 +157,40 @@ def test_connect_four_full_size():
     check_invariants({k: v[:64] for k, v in got.arrays.items()})
 
 
+def test_othello_weighted_full_size():
+    """BASELINE.json configs[2] per-GPU share at 8 GPUs: 512 envs x 200 simulations, N = 400, WeightedMCTS backup."""
+    s = Schedule(game=SN.make_game("othello", 3000), B=512, N=400, S=200, moves=2, temperature=1.0, weighted=True)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), "othello weighted full")
+
+
+def test_2048_full_size_positive_discount():
+    """BASELINE.json configs[4] per-GPU share: 2048 envs x 100 simulations, N = 200, discount +1, programmatic launches."""
+    s = Schedule(game=SN.make_game("2048", 5000), B=2048, N=200, S=100, moves=3, temperature=1.0, discount=1.0, programmatic=True)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), "2048 full")
+
+
+def test_go_9x9_full_depth_reduced_batch():
+    """BASELINE.json configs[3] tree shape at full depth (N = 1600, 800 simulations, 82-way, 4 KB embedding rows, paths far
+    beyond the 32-level ring) on 48 envs -- the oracle needs seconds for that; the full 1024-env batch is checked through
+    its invariants below."""
+    s = Schedule(game=SN.make_game("go_9x9", 4000), B=48, N=1600, S=800, moves=2, temperature=1.0)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=False), "go_9x9 full depth")
+
+
+def test_go_9x9_full_size_invariants():
+    """configs[3] per-GPU share (1024 envs x 800 simulations): structural invariants of the reference's trees, the derived
+    tables against a from-scratch rebuild, the best-table against a re-evaluation of the selector (run_cuda_selfplay checks
+    the last two), and visit-count conservation: n[root] = 1 + simulations landed below it."""
+    s = Schedule(game=SN.make_game("go_9x9", 4001), B=1024, N=1600, S=800, moves=1, temperature=1.0, persist_tree=False)
+    got = run_cuda_selfplay(s, graph=True)  # persist_tree=False: the tree is reset after the move ...
+    assert (got.arrays["next_free_idx"] == 0).all() and (got.arrays["parents"] == -1).all() and not got.arrays["n"].any()
+    assert np.allclose(got.pw.sum(-1), 1.0, atol=1e-5) and (got.pw >= 0).all()  # ... and the move's policy weights are visit shares
+    s2 = Schedule(game=SN.make_game("go_9x9", 4001), B=1024, N=1600, S=800, moves=1, temperature=1.0)
+    got2 = run_cuda_selfplay(s2, graph=True)
+    check_invariants({k: v[:96] for k, v in got2.arrays.items()})
+    assert np.array_equal(got.actions, got2.actions) and np.array_equal(got.pw, got2.pw)  # persistence does not change move 0
+
+
 def test_division_sequence_is_ieee_exact():
     """The select kernel's straight-line division (div_core) equals div.rn bit-for-bit on 2^30 operand pairs."""
     import torch
