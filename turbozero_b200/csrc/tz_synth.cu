@@ -21,6 +21,15 @@ constexpr int MAX_NC = 16;
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_programmatic{0};  // tz_synth_set_programmatic
 
+#ifdef TZ_PROFILE  // diagnostic build (libtz_synth_prof.so): per-launch timeline of k_leaf, see scripts/timeline.py
+__device__ unsigned long long g_tl[4 * 1024];  // {first warp in, last warp past griddepcontrol.wait, last warp out, -}
+__device__ __forceinline__ unsigned long long tl_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+std::atomic<uint32_t> g_tl_seq{0};
+#define TZ_TL(op, slot, k) do { if ((threadIdx.x & 31) == 0) op(&g_tl[4 * (slot) + (k)], tl_now()); } while (0)
+#else
+#define TZ_TL(op, slot, k) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t fkey(float x) {
   uint32_t u = __float_as_uint(x);
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -112,9 +121,12 @@ __global__ void __launch_bounds__(THREADS) k_root(const TzSynthGame g, const int
 __global__ void __launch_bounds__(THREADS) k_leaf(const TzSynthGame g, const int B, const int32_t* __restrict__ parent_core,
                                                 const int32_t* __restrict__ action, float* __restrict__ policy,
                                                 float* __restrict__ value, uint8_t* __restrict__ terminated, int32_t* new_core,
-                                                uint8_t* new_payload, const int pdl) {
+                                                uint8_t* new_payload, const int pdl_and_slot) {
+  const int pdl = pdl_and_slot & 1;
+  [[maybe_unused]] const int tl_slot = pdl_and_slot >> 1;  // diagnostic build: timeline slot of this launch
   const int b = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
+  TZ_TL(atomicMin, tl_slot, 0);
   const int F = g.F, nc = (F + 31) >> 5;
   const int32_t* pc = parent_core + 4 * (size_t)b;
   // Programmatic dependent launch, the form TzSearchCfg.programmatic asks of a leaf kernel: wait for the preceding
@@ -127,6 +139,7 @@ __global__ void __launch_bounds__(THREADS) k_leaf(const TzSynthGame g, const int
                  : "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
+  TZ_TL(atomicMax, tl_slot, 1);
   const uint32_t h2 = tz_synth_step_h((uint32_t)pc[0], (uint32_t)action[b]);
   const int d2 = pc[1] + 1;
   const int term = tz_synth_terminal(h2, d2, g.tau1024, g.max_depth);
@@ -145,6 +158,7 @@ __global__ void __launch_bounds__(THREADS) k_leaf(const TzSynthGame g, const int
     terminated[b] = (uint8_t)term;
   }
   write_state(g, h2, d2, 1 - pc[2], new_core + 4 * (size_t)b, new_payload ? new_payload + (size_t)b * g.payload_bytes : nullptr, lane);
+  TZ_TL(atomicMax, tl_slot, 2);
 }
 
 __global__ void __launch_bounds__(THREADS) k_env_step(const TzSynthGame g, const int B, const int env_offset,
@@ -190,6 +204,20 @@ extern "C" {
 
 uint64_t tz_synth_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
+#ifdef TZ_PROFILE
+int tz_synth_debug_timeline(unsigned long long* out, int reset) {  // diagnostic build only: 1024 rows of 4
+  const cudaError_t e = cudaMemcpyFromSymbol(out, g_tl, sizeof(g_tl));
+  if (e != cudaSuccess || !reset) return (int)e;
+  static unsigned long long init[4 * 1024];
+  for (int i = 0; i < 1024; ++i) {
+    init[4 * i + 0] = ~0ull;
+    init[4 * i + 1] = init[4 * i + 2] = init[4 * i + 3] = 0ull;
+  }
+  g_tl_seq.store(0);
+  return (int)cudaMemcpyToSymbol(g_tl, init, sizeof(init));
+}
+#endif
+
 int tz_synth_set_programmatic(int on) { return g_programmatic.exchange(on ? 1 : 0, std::memory_order_relaxed); }
 
 int tz_synth_init_states(const TzSynthGame* g, int B, int env_offset, const int32_t* episode, int32_t* core,
@@ -217,6 +245,11 @@ int tz_synth_leaf(const TzSynthGame* g, int B, const int32_t* parent_core, const
   if (rc) return rc;
   if (!parent_core || !action || !policy || !value || !terminated || !new_core) return TZ_EINVAL;
   if (g->payload_bytes > 0 && !new_payload) return TZ_EINVAL;
+#ifdef TZ_PROFILE
+  const int tl_slot = (int)((g_tl_seq.fetch_add(1, std::memory_order_relaxed) & 1023u) << 1);
+#else
+  const int tl_slot = 0;
+#endif
   if (g_programmatic.load(std::memory_order_relaxed)) {
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid_for(B));
@@ -227,12 +260,12 @@ int tz_synth_leaf(const TzSynthGame* g, int B, const int32_t* parent_core, const
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, k_leaf, *g, B, parent_core, action, policy, value, terminated, new_core, new_payload, 1);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, k_leaf, *g, B, parent_core, action, policy, value, terminated, new_core, new_payload, 1 | tl_slot);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e == cudaSuccess ? TZ_OK : (int)e;
   }
   k_leaf<<<grid_for(B), THREADS, 0, (cudaStream_t)stream>>>(*g, B, parent_core, action, policy, value, terminated, new_core,
-                                                          new_payload, 0);
+                                                          new_payload, 0 | tl_slot);
   return status();
 }
 
