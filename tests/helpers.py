@@ -307,7 +307,7 @@ def run_cuda_api(s: Schedule, fused: bool = True, snapshots: bool = False) -> Re
         actions[m], pw[m] = act.cpu().numpy(), pwm.cpu().numpy()
         if snapshots:
             snaps.append(tree_to_numpy(tree))
-        assert_best_table_consistent(tree, ev, f"after the search of move {m}")
+        assert_best_table_consistent(tree, ev, f"after the search of move {m}", expect_known=s.S > 0)
         assert_child_stats_consistent(tree, f"after the search of move {m}")
         game.env_step(state, act, episode, reset_flag, s.env_offset)
         ev.step(tree, act, reset_mask=reset_flag)

@@ -157,6 +157,39 @@ def test_connect_four_full_size():
     check_invariants({k: v[:64] for k, v in got.arrays.items()})
 
 
+EDGE = {
+    # one tree, one action, odd capacity: every walk is a chain; the tree fills up (tree.py:116-131) and keeps backing up
+    "F1_N7_B1": dict(game=G(F=1, payload_bytes=1, rho256=0, tau1024=0, max_depth=1000, seed=51), B=1, N=7, S=12, moves=3, temperature=1.0),
+    # capacity 1: only the root ever exists; every expansion is dropped
+    "N1": dict(game=G(F=5, payload_bytes=3, rho256=200, tau1024=0, max_depth=50, seed=52), B=3, N=1, S=6, moves=3, temperature=1.0),
+    # capacity 2 and an odd batch
+    "N2_B7": dict(game=G(F=4, payload_bytes=0, rho256=200, tau1024=30, max_depth=50, seed=53), B=7, N=2, S=9, moves=4, temperature=0.0),
+    # two register chunks with one action in the second (F = 33), odd capacity (unaligned best-table rows)
+    "F33_N33": dict(game=G(F=33, payload_bytes=9, rho256=120, tau1024=10, max_depth=40, seed=54), B=5, N=33, S=40, moves=3, temperature=1.0),
+    # the widest dispatch (16 chunks)
+    "F512": dict(game=G(F=512, payload_bytes=4, rho256=64, tau1024=4, max_depth=30, seed=55), B=2, N=24, S=30, moves=2, temperature=1.0),
+    # a single simulation per move, and none at all (root only: uniform policy weights, mcts.py:279)
+    "S1": dict(game=G(F=6, payload_bytes=2, rho256=200, tau1024=20, max_depth=30, seed=56), B=4, N=16, S=1, moves=5, temperature=1.0),
+    "S0": dict(game=G(F=6, payload_bytes=2, rho256=200, tau1024=20, max_depth=30, seed=57), B=4, N=16, S=0, moves=3, temperature=1.0),
+    # weighted backup on a two-action tree with odd capacity and argmax weights
+    "weighted_F2_qT0": dict(game=G(F=2, payload_bytes=0, rho256=256, tau1024=0, max_depth=60, seed=58), B=3, N=45, S=50, moves=2,
+                            temperature=1.0, weighted=True, q_temperature=0.0),
+}
+
+
+@pytest.mark.parametrize("name", list(EDGE))
+def test_edge_shapes_python_api_vs_oracle(name):
+    s = Schedule(**EDGE[name])
+    _compare(run_c_stepwise(s), run_cuda_api(s, fused=True), name)
+
+
+@pytest.mark.parametrize("name", [n for n in EDGE if n != "weighted_F2_qT0"])
+@pytest.mark.parametrize("graph", [False, True])
+def test_edge_shapes_c_loop_vs_oracle(name, graph):
+    s = Schedule(**EDGE[name], programmatic=graph)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=graph), name)
+
+
 def test_othello_weighted_full_size():
     """BASELINE.json configs[2] per-GPU share at 8 GPUs: 512 envs x 200 simulations, N = 400, WeightedMCTS backup."""
     s = Schedule(game=SN.make_game("othello", 3000), B=512, N=400, S=200, moves=2, temperature=1.0, weighted=True)
