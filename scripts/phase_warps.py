@@ -56,3 +56,4 @@ def run(name, B, S, N):
 
 if __name__ == "__main__":
     run("connect_four", 1024, 128, 256)
+    run("go_9x9", 1024, 800, 1600)
