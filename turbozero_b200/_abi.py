@@ -5,6 +5,7 @@ There is NO fallback: if the CUDA library is missing or a call fails, an excepti
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 TZ_MAX_EMB = 24
@@ -140,7 +141,8 @@ def lib() -> C.CDLL:
     """libtz_b200.so (loaded once)."""
     global _lib
     if _lib is None:
-        _lib = _load("libtz_b200.so", TZ_SYMBOLS)
+        # TZ_B200_LIB: file name of an alternative build in lib/ (diagnostic / experimental builds of the same ABI)
+        _lib = _load(os.environ.get("TZ_B200_LIB", "libtz_b200.so"), TZ_SYMBOLS)
         if _lib.tz_abi_version() != TZ_ABI_VERSION:
             raise TzError("libtz_b200.so ABI version mismatch")
     return _lib
