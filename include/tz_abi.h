@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define TZ_ABI_VERSION 6
+#define TZ_ABI_VERSION 7
 #define TZ_MAX_EMB 24 /* max number of embedding pytree leaves per node */
 #define TZ_PATH_CAP 32 /* path slots kept per tree between select and backprop */
 #define TZ_PATH_STRIDE (2 * TZ_PATH_CAP + 2) /* ints per tree in TzWork.path: nodes[32], actions[32], length, end child */
@@ -86,6 +86,14 @@ typedef struct TzTree {
 #define TZ_SEL_PUCT 0        /* PUCTSelector :61-116 */
 #define TZ_SEL_MUZERO_PUCT 1 /* MuZeroPUCTSelector :119-177 (intended maths) */
 
+/* q_transform of a selector (action_selection.py:70,128 constructor argument `q_transform`): a REGISTRY of device
+ * functors, selected by id.  Adding one = a new id here, a case in q_transform_apply (csrc/tz_kernels.cu), the same case in
+ * both oracles (oracle/mcts_numpy.py, oracle/tz_oracle.c) and a descriptor in turbozero_b200/action_selection.py
+ * (register_q_transform); arbitrary Python callables cannot run inside the kernel. */
+#define TZ_QT_NORMALIZE 0 /* normalize_q_values, action_selection.py:10-32 (the default) */
+#define TZ_QT_IDENTITY 1  /* lambda q, n, parent_q, eps: q -- the discounted child values as they are (0 for missing children) */
+#define TZ_QT_COUNT 2
+
 typedef struct TzSearchCfg {
   int32_t selector;      /* TZ_SEL_* */
   float c;               /* PUCTSelector.c  (action_selection.py:67) */
@@ -110,6 +118,10 @@ typedef struct TzSearchCfg {
                             satisfy the first form).  Pays when that kernel is short (a waiting grid is resident and takes
                             issue slots from it): measured +12 % on configs[1] with the 2 us synthetic leaf, -7 % on the
                             go_9x9 shape whose leaf runs 10 us (profiles/).  0: ordinary stream-ordered launches. */
+  int32_t q_transform;   /* TZ_QT_*: the selector's q_transform (action_selection.py:70,109) */
+  int32_t sim_warps;     /* warps that cooperate on ONE tree in the per-simulation kernel: 0 = library's choice (1 for narrow
+                            trees, 4 for trees with more than 32 actions), 1 = one warp per tree, 2 / 4 / 8 = a CTA per tree
+                            whose warps score the path levels side by side (results are identical for every value) */
 } TzSearchCfg;
 
 /* Per-simulation exchange buffers between the kernels and the host framework's
@@ -132,7 +144,12 @@ typedef struct TzWork {
                                ring does; without it (NULL) levels above the ring are reached by chasing parents[], one
                                dependent round trip each.  path_spill_cap >= max_nodes - 32 covers every possible path. */
   int32_t path_spill_cap;   /* entries per tree in path_spill */
-  int32_t pad;
+  int32_t timeline_slots;   /* rows of `timeline` (a power of two), 0 = none */
+  uint64_t* timeline;       /* optional [timeline_slots,4] measurement record of the per-simulation launches that use this
+                               TzWork: row (launch sequence number mod timeline_slots, see tz_launch_seq) holds %globaltimer
+                               nanoseconds {first warp in (min), last warp has its leaf results (max), last warp out (max),
+                               unused}.  The caller initialises rows to {~0, 0, 0, 0}.  Costs three reductions per warp when
+                               set; NULL = no record.  bench.py uses it to time the kernel INSIDE the step it describes. */
 } TzWork;
 
 int tz_abi_version(void);
@@ -201,6 +218,11 @@ int tz_selftest_best(const TzTree* t, const TzSearchCfg* cfg, uint64_t* out_dev,
 
 /* Number of kernels this library has launched since load (for bench accounting). */
 uint64_t tz_launch_count(void);
+
+/* Sequence number the NEXT per-simulation launch (tz_select / tz_expand_backprop[_select]) will carry; a launch writes row
+ * (its sequence number mod timeline_slots) of TzWork.timeline.  Launches captured into a CUDA graph keep the number they
+ * were captured with. */
+uint64_t tz_launch_seq(void);
 
 #ifdef __cplusplus
 }

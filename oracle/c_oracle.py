@@ -52,10 +52,10 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 def make_cfg(selector=0, c=1.0, c1=1.25, c2=19652.0, epsilon=1e-8, discount=-1.0, weighted=False, q_temperature=1.0,
-             fma_backup=False) -> TzSearchCfg:
+             fma_backup=False, q_transform=0) -> TzSearchCfg:
     inv_t = float(np.float32(1.0 / q_temperature)) if q_temperature > 0 else 0.0
     return TzSearchCfg(selector=selector, c=c, c1=c1, c2=c2, epsilon=epsilon, discount=discount, weighted=int(weighted),
-                       inv_q_temperature=inv_t, fma_backup=int(fma_backup))
+                       inv_q_temperature=inv_t, fma_backup=int(fma_backup), q_transform=int(q_transform))
 
 
 @dataclass

@@ -211,6 +211,7 @@ class SearchCfg:
     weighted: bool = False
     q_temperature: float = 1.0  # weighted_mcts.py:25
     fma_backup: bool = False
+    q_transform: int = 0  # include/tz_abi.h TZ_QT_*: 0 normalize_q_values (action_selection.py:70), 1 identity
 
 
 def normalize_q_values(q_values, child_n, parent_q, epsilon) -> np.ndarray:
@@ -222,13 +223,23 @@ def normalize_q_values(q_values, child_n, parent_q, epsilon) -> np.ndarray:
     return ((completed - mn).astype(f32) / denom).astype(f32)
 
 
+def q_transform(kind: int, q_values, child_n, parent_q, epsilon) -> np.ndarray:
+    """The registry of q_transform functors (include/tz_abi.h TZ_QT_*), the `q_transform` constructor argument of
+    action_selection.py:70,128."""
+    if kind == 0:
+        return normalize_q_values(q_values, child_n, parent_q, epsilon)
+    if kind == 1:  # lambda q, n, parent_q, eps: q
+        return q_values
+    raise ValueError(f"unknown q_transform {kind}")
+
+
 def select_action(tree: Tree, index: int, cfg: SearchCfg) -> int:
     """PUCTSelector.__call__ action_selection.py:91-116 / MuZeroPUCTSelector.__call__ :150-177."""
     node_q, node_n, node_p = tree.q[index], tree.n[index], tree.p[index]
     q_values = get_child_data(tree, tree.q, index).astype(f32)
     dq = (q_values * f32(cfg.discount)).astype(f32)
     n_values = get_child_data(tree, tree.n, index).astype(i32)
-    qn = normalize_q_values(dq, n_values, node_q, cfg.epsilon)
+    qn = q_transform(cfg.q_transform, dq, n_values, node_q, cfg.epsilon)  # self.q_transform(...), :109
     sq = np.sqrt(f32(node_n))
     denom = (n_values + i32(1)).astype(f32)
     if cfg.selector == SEL_PUCT:

@@ -80,8 +80,6 @@ def _tree_arrays(tree, payload_bytes: int) -> dict:
 
 def run_reference(s, snapshots: bool = False):
     """`s` is a tests/helpers.Schedule.  Returns (arrays, actions, pw, snapshots) with trees stacked over the batch."""
-    if s.selector != 0:
-        raise ValueError("MuZeroPUCTSelector cannot run in the reference (arity bug, action_selection.py:169)")
     if s.fma_backup:
         raise ValueError("fma_backup is a what-if about XLA, not reference source behaviour")
     R = load_reference()
@@ -118,7 +116,22 @@ def run_reference(s, snapshots: bool = False):
         return state(h2, d2, 1 - player), metadata(h2, d2, 1 - player, g.terminal(h2, d2))
 
     base = R["weighted_mcts"].WeightedMCTS if s.weighted else R["mcts"].MCTS
-    kw = dict(eval_fn=eval_fn, action_selector=R["action_selection"].PUCTSelector(c=s.c), branching_factor=F, max_nodes=s.N,
+    AS = R["action_selection"]
+    # the `q_transform` constructor argument (action_selection.py:70,128): the reference's own normalize_q_values, or the
+    # identity (TZ_QT_IDENTITY) as a plain Python callable -- both handed to the reference's UNMODIFIED selector classes
+    qt4 = {0: AS.normalize_q_values, 1: (lambda q, n, parent_q, eps: q)}[getattr(s, "q_transform", 0)]
+    if s.selector == 0:
+        selector = AS.PUCTSelector(c=s.c, q_transform=qt4)
+    else:
+        # MuZeroPUCTSelector.__call__ passes FIVE positional arguments -- (discounted q, q, n, parent q, epsilon) -- to a
+        # four-argument q_transform (action_selection.py:169), so it cannot run with its default.  The "arity fix" lives
+        # HERE, not in the reference source: a five-argument adapter that drops the un-discounted q and forwards to the
+        # four-argument function.  Fixtures made this way carry "arityfix" in their name.
+        def qt5(discounted_q, _q, n, parent_q, eps):
+            return qt4(discounted_q, n, parent_q, eps)
+
+        selector = AS.MuZeroPUCTSelector(c1=s.c1, c2=s.c2, q_transform=qt5)
+    kw = dict(eval_fn=eval_fn, action_selector=selector, branching_factor=F, max_nodes=s.N,
               num_iterations=s.S, discount=s.discount, temperature=s.temperature, tiebreak_noise=s.tiebreak_noise,
               persist_tree=s.persist_tree)
     if s.weighted:

@@ -125,6 +125,8 @@ static int select_action(const View* v, int i, const TzSearchCfg* cfg) {
   int F = v->F;
   child_qn(v, i, cfg->discount, dq, cn);
   normalize_q(dq, cn, v->q[i], cfg->epsilon, qn, F);
+  if (cfg->q_transform == TZ_QT_IDENTITY) /* the q_transform registry (include/tz_abi.h TZ_QT_*), action_selection.py:70,109 */
+    for (int a = 0; a < F; ++a) qn[a] = dq[a];
   float sq = sqrtf((float)v->n[i]);
   const float* p = v->p + (size_t)i * F;
   float log_term = 0.0f;

@@ -60,6 +60,17 @@ CASES = {
     # deep narrow trees, fractional discount, c != 1
     "deep_discount09": dict(game=G(F=5, payload_bytes=3, rho256=230, tau1024=0, max_depth=100, seed=8), B=2, N=200, S=150,
                             moves=2, temperature=1.0, discount=0.9, c=2.5),
+    # MuZeroPUCTSelector (action_selection.py:119-177), run through the reference's unmodified class with a five-argument
+    # adapter around its own normalize_q_values as `q_transform` (the arity bug of :169; see oracle/ref_via_shim.py)
+    "muzero_puct_arityfix": dict(game=G(F=7, payload_bytes=8, rho256=230, tau1024=12, max_depth=42, seed=21), B=3, N=64, S=48,
+                                 moves=4, temperature=1.0, selector=1, c1=1.25, c2=19652.0),
+    "muzero_puct_arityfix_wide_small_c2": dict(game=G(F=40, payload_bytes=4, rho256=120, tau1024=6, max_depth=60, seed=22), B=2,
+                                               N=72, S=60, moves=3, temperature=0.0, selector=1, c1=0.7, c2=11.0),
+    # PUCTSelector with a different registered q_transform: the identity (include/tz_abi.h TZ_QT_IDENTITY)
+    "puct_identity_qtransform": dict(game=G(F=7, payload_bytes=8, rho256=230, tau1024=12, max_depth=42, seed=23), B=3, N=64, S=48,
+                                     moves=4, temperature=1.0, q_transform=1),
+    "puct_identity_qtransform_wide": dict(game=G(F=36, payload_bytes=0, rho256=140, tau1024=6, max_depth=60, seed=24), B=2, N=60,
+                                          S=50, moves=3, temperature=1.0, q_transform=1, discount=0.9),
     "very_deep_F2": dict(game=G(F=2, payload_bytes=4, rho256=0, tau1024=0, max_depth=1000, seed=12), B=2, N=120, S=100, moves=2,
                          temperature=1.0, discount=0.97),
 }

@@ -36,6 +36,9 @@ class Schedule:
     weighted: bool = False
     q_temperature: float = 1.0
     selector: int = 0
+    c1: float = 1.25  # MuZeroPUCTSelector (selector == 1)
+    c2: float = 19652.0
+    q_transform: int = 0  # include/tz_abi.h TZ_QT_*
     discount: float = -1.0
     c: float = 1.0
     fma_backup: bool = False
@@ -55,12 +58,12 @@ class Schedule:
                          if (self.weighted and self.q_temperature == 0) else None)
 
     def np_cfg(self) -> M.SearchCfg:
-        return M.SearchCfg(selector=self.selector, c=self.c, discount=self.discount, weighted=self.weighted,
-                           q_temperature=self.q_temperature, fma_backup=self.fma_backup)
+        return M.SearchCfg(selector=self.selector, c=self.c, c1=self.c1, c2=self.c2, discount=self.discount, weighted=self.weighted,
+                           q_temperature=self.q_temperature, fma_backup=self.fma_backup, q_transform=self.q_transform)
 
     def c_cfg(self):
-        return CO.make_cfg(selector=self.selector, c=self.c, discount=self.discount, weighted=self.weighted,
-                           q_temperature=self.q_temperature, fma_backup=self.fma_backup)
+        return CO.make_cfg(selector=self.selector, c=self.c, c1=self.c1, c2=self.c2, discount=self.discount, weighted=self.weighted,
+                           q_temperature=self.q_temperature, fma_backup=self.fma_backup, q_transform=self.q_transform)
 
     def c_game(self):
         g = self.game
@@ -266,7 +269,8 @@ def make_cuda_evaluator(s: Schedule, game):
     import turbozero_b200 as tz
     from turbozero_b200.synthetic import make_synthetic_evaluator
 
-    sel = tz.PUCTSelector(c=s.c) if s.selector == 0 else tz.MuZeroPUCTSelector()
+    qt = {0: tz.normalize_q_values, 1: "identity"}[s.q_transform]
+    sel = tz.PUCTSelector(c=s.c, q_transform=qt) if s.selector == 0 else tz.MuZeroPUCTSelector(c1=s.c1, c2=s.c2, q_transform=qt)
     base = tz.WeightedMCTS if s.weighted else tz.MCTS
     kw = dict(action_selector=sel, max_nodes=s.N, num_iterations=s.S, discount=s.discount, temperature=s.temperature,
               tiebreak_noise=s.tiebreak_noise, persist_tree=s.persist_tree)

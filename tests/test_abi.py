@@ -59,7 +59,7 @@ def test_product_library_does_not_depend_on_oracle_or_synth(built):
 
 def test_abi_version_and_strerror(built):
     lib = built.lib()
-    assert lib.tz_abi_version() == built.TZ_ABI_VERSION == 6
+    assert lib.tz_abi_version() == built.TZ_ABI_VERSION == 7
     assert lib.tz_strerror(0) == b"ok"
     assert b"invalid" in lib.tz_strerror(-1)
     assert b"not supported" in lib.tz_strerror(-2)
@@ -74,8 +74,8 @@ def test_struct_layouts_match_the_c_compiler(built, tmp_path):
 int main(void) {
   printf("%zu %zu %zu %zu %zu\n", sizeof(TzTree), sizeof(TzSearchCfg), sizeof(TzWork), sizeof(TzSynthGame), sizeof(TzSynthCtx));
   printf("%zu %zu %zu %zu %zu %zu %zu\n", offsetof(TzTree, next_free_idx), offsetof(TzTree, child_stats), offsetof(TzTree, best), offsetof(TzTree, sel_state), offsetof(TzTree, emb), offsetof(TzTree, emb_row_bytes), offsetof(TzTree, stats));
-  printf("%zu %zu %zu %zu\n", offsetof(TzSearchCfg, discount), offsetof(TzSearchCfg, inv_q_temperature), offsetof(TzSearchCfg, fma_backup), offsetof(TzSearchCfg, programmatic));
-  printf("%zu %zu %zu %zu %zu %zu\n", offsetof(TzWork, emb_parent), offsetof(TzWork, policy), offsetof(TzWork, emb_new), offsetof(TzWork, path), offsetof(TzWork, path_spill), offsetof(TzWork, path_spill_cap));
+  printf("%zu %zu %zu %zu %zu %zu\n", offsetof(TzSearchCfg, discount), offsetof(TzSearchCfg, inv_q_temperature), offsetof(TzSearchCfg, fma_backup), offsetof(TzSearchCfg, programmatic), offsetof(TzSearchCfg, q_transform), offsetof(TzSearchCfg, sim_warps));
+  printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", offsetof(TzWork, emb_parent), offsetof(TzWork, policy), offsetof(TzWork, emb_new), offsetof(TzWork, path), offsetof(TzWork, path_spill), offsetof(TzWork, path_spill_cap), offsetof(TzWork, timeline_slots), offsetof(TzWork, timeline));
   return 0;
 }''')
     exe = tmp_path / "layout"
@@ -84,8 +84,8 @@ int main(void) {
     T, S, W = built.TzTree, built.TzSearchCfg, built.TzWork
     assert lines[0].split() == [str(C.sizeof(x)) for x in (T, S, W, built.TzSynthGame, built.TzSynthCtx)]
     assert lines[1].split() == [str(getattr(T, f).offset) for f in ("next_free_idx", "child_stats", "best", "sel_state", "emb", "emb_row_bytes", "stats")]
-    assert lines[2].split() == [str(getattr(S, f).offset) for f in ("discount", "inv_q_temperature", "fma_backup", "programmatic")]
-    assert lines[3].split() == [str(getattr(W, f).offset) for f in ("emb_parent", "policy", "emb_new", "path", "path_spill", "path_spill_cap")]
+    assert lines[2].split() == [str(getattr(S, f).offset) for f in ("discount", "inv_q_temperature", "fma_backup", "programmatic", "q_transform", "sim_warps")]
+    assert lines[3].split() == [str(getattr(W, f).offset) for f in ("emb_parent", "policy", "emb_new", "path", "path_spill", "path_spill_cap", "timeline_slots", "timeline")]
 
 
 def test_argument_validation_needs_no_gpu(built):

@@ -24,7 +24,7 @@ def test_mcts_constructor_defaults_and_config():  # mcts.py:19-68
 
 def test_selector_registry():  # action_selection.py:35-177
     p = tz.PUCTSelector(c=2.5, epsilon=1e-6).kernel_params()
-    assert p == dict(selector=_abi.TZ_SEL_PUCT, c=2.5, c1=0.0, c2=1.0, epsilon=1e-6)
+    assert p == dict(selector=_abi.TZ_SEL_PUCT, c=2.5, c1=0.0, c2=1.0, epsilon=1e-6, q_transform=_abi.TZ_QT_NORMALIZE)
     m = tz.MuZeroPUCTSelector()
     assert m.get_config() == {"c1": 1.25, "c2": 19652, "q_transform": "normalize_q_values", "epsilon": 1e-8}
     assert m.kernel_params()["selector"] == _abi.TZ_SEL_MUZERO_PUCT
@@ -35,8 +35,37 @@ def test_selector_registry():  # action_selection.py:35-177
 
     with pytest.raises(NotImplementedError, match="no device implementation"):
         make(action_selector=Custom())  # no CPU fallback: arbitrary Python selectors are refused at construction
-    with pytest.raises(NotImplementedError):
-        tz.PUCTSelector(q_transform=lambda *a: a[0])
+    with pytest.raises(NotImplementedError, match="register_q_transform"):
+        tz.PUCTSelector(q_transform=lambda *a: a[0])  # an unregistered Python callable cannot run in the kernel
+
+
+def test_q_transform_registry_and_host_functions():  # action_selection.py:10-32, :70, :128
+    # the registered transforms are selectable by function object or by name and land in TzSearchCfg.q_transform
+    assert tz.PUCTSelector(q_transform=tz.identity_q_values).kernel_params()["q_transform"] == _abi.TZ_QT_IDENTITY
+    assert tz.MuZeroPUCTSelector(q_transform="identity").kernel_params()["q_transform"] == _abi.TZ_QT_IDENTITY
+    assert tz.PUCTSelector(q_transform="identity").get_config()["q_transform"] == "identity"
+    assert make(action_selector=tz.PUCTSelector(q_transform="identity"))._cfg().q_transform == _abi.TZ_QT_IDENTITY
+    assert make()._cfg().q_transform == _abi.TZ_QT_NORMALIZE
+    # normalize_q_values is host-callable like the reference's; SURVEY.md 8c KA-2: dq = [0.4, -0, -0], only child 0 visited
+    q = tz.normalize_q_values(torch.tensor([0.4, -0.0, -0.0]), torch.tensor([2, 0, 0]), 0.2, 1e-8)
+    assert torch.equal(q, torch.tensor([1.0, 0.0, 0.0]))
+    # batched, and identical to the NumPy oracle's restatement of the same lines
+    import numpy as np
+    from oracle import mcts_numpy as M
+
+    rng = np.random.default_rng(0)
+    qv = rng.standard_normal((5, 9)).astype(np.float32)
+    nv = rng.integers(0, 3, (5, 9)).astype(np.int32)
+    pq = rng.standard_normal((5,)).astype(np.float32)
+    got = tz.normalize_q_values(torch.from_numpy(qv), torch.from_numpy(nv), torch.from_numpy(pq), 1e-8).numpy()
+    for i in range(5):
+        assert np.array_equal(got[i], M.normalize_q_values(qv[i], nv[i], pq[i], 1e-8))
+    assert torch.equal(tz.identity_q_values(torch.from_numpy(qv), None, None, 0.0), torch.from_numpy(qv))
+    # a user-registered name maps to an existing device functor id
+    def my_identity(q, n, parent_q, eps):
+        return q
+    tz.register_q_transform(my_identity, _abi.TZ_QT_IDENTITY)
+    assert tz.PUCTSelector(q_transform=my_identity).kernel_params()["q_transform"] == _abi.TZ_QT_IDENTITY
 
 
 def test_search_cfg_struct_from_evaluator():

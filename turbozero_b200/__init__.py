@@ -1,6 +1,7 @@
 """turbozero_b200 -- turbozero's batched MCTS hot path as hand-written sm_100a CUDA kernels behind the
 reference's own Evaluator / MCTS API.  See DESIGN.md and INTEGRATION.md."""
-from .action_selection import MCTSActionSelector, MuZeroPUCTSelector, PUCTSelector, normalize_q_values
+from .action_selection import (MCTSActionSelector, MuZeroPUCTSelector, PUCTSelector, identity_q_values, normalize_q_values,
+                               register_q_transform)
 from .alphazero import AlphaZero
 from .collect import CollectionState, collect
 from .common import (GameFrame, TwoPlayerGameState, merge_topk, partition, shard_slice, step_env_and_evaluator,
@@ -14,7 +15,8 @@ from .weighted_mcts import WeightedMCTS
 
 __all__ = [
     "MCTS", "WeightedMCTS", "AlphaZero", "MCTSOutput", "TraversalState", "Evaluator", "EvalOutput",
-    "MCTSActionSelector", "PUCTSelector", "MuZeroPUCTSelector", "normalize_q_values",
+    "MCTSActionSelector", "PUCTSelector", "MuZeroPUCTSelector", "normalize_q_values", "identity_q_values",
+    "register_q_transform",
     "Tree", "MCTSTree", "MCTSNode", "WeightedMCTSNode", "init_tree", "StepMetadata",
     "partition", "shard_slice", "step_env_and_evaluator", "merge_topk",
     "TwoPlayerGameState", "GameFrame", "two_player_game_step", "two_player_game",

@@ -12,9 +12,11 @@ TZ_MAX_EMB = 24
 TZ_PATH_CAP = 32
 TZ_PATH_STRIDE = 2 * TZ_PATH_CAP + 2
 TZ_SEL_STATE_WORDS = 8
-TZ_ABI_VERSION = 6
+TZ_ABI_VERSION = 7
 TZ_SEL_PUCT = 0
 TZ_SEL_MUZERO_PUCT = 1
+TZ_QT_NORMALIZE = 0
+TZ_QT_IDENTITY = 1
 
 LIB_DIR = Path(__file__).resolve().parent / "lib"
 
@@ -36,6 +38,7 @@ class TzSearchCfg(C.Structure):
         ("selector", C.c_int32), ("c", C.c_float), ("c1", C.c_float), ("c2", C.c_float),
         ("epsilon", C.c_float), ("discount", C.c_float), ("weighted", C.c_int32),
         ("inv_q_temperature", C.c_float), ("fma_backup", C.c_int32), ("programmatic", C.c_int32),
+        ("q_transform", C.c_int32), ("sim_warps", C.c_int32),
     ]
 
 
@@ -46,7 +49,8 @@ class TzWork(C.Structure):
         ("policy", C.c_void_p), ("value", C.c_void_p), ("terminated", C.c_void_p),
         ("emb_new", C.c_void_p * TZ_MAX_EMB),
         ("backprop_noise", C.c_void_p), ("path", C.c_void_p),
-        ("path_spill", C.c_void_p), ("path_spill_cap", C.c_int32), ("pad", C.c_int32),
+        ("path_spill", C.c_void_p), ("path_spill_cap", C.c_int32), ("timeline_slots", C.c_int32),
+        ("timeline", C.c_void_p),
     ]
 
 
@@ -82,6 +86,7 @@ TZ_SYMBOLS = {
     "tz_abi_version": (C.c_int, []),
     "tz_strerror": (C.c_char_p, [C.c_int]),
     "tz_launch_count": (C.c_uint64, []),
+    "tz_launch_seq": (C.c_uint64, []),
     "tz_tree_init": (C.c_int, [_P(TzTree), _vp]),
     "tz_rebuild_child_stats": (C.c_int, [_P(TzTree), _vp]),
     "tz_set_root": (C.c_int, [_P(TzTree), _vp, _vp, _P(_vp), _vp]),

@@ -10,8 +10,10 @@
 //   tree  = next_free_idx[B], parents[B,N], edge_map[B,N,F], n[B,N], p[B,N,F], q[B,N], terminated[B,N],
 //           child_stats[B,N,F,4], best[B,N,2], sel_state[B,8], (r[B,N] if weighted), emb_0 .. emb_{K-1} [B,N,...]
 //   The three derived tables are extra leaves the binding adds to the MCTSTree pytree (allocated by init, see ffi_jax.py).
-//   Mutating handlers take the tree as operands AND as results, aliased one to one (input_output_aliases), and work on
-//   the result buffers.
+//   Mutating handlers take the tree as operands AND as results and work on the result buffers.  With
+//   input_output_aliases (jax >= 0.4.38) XLA hands the same buffer in and out; without it (jax 0.4.35-0.4.37, whose
+//   ffi_call has no aliasing argument) the result buffers arrive UNINITIALISED, so every mutating handler first copies
+//   each operand into its result wherever the two pointers differ (CopyIn below; a no-op when aliased).
 #include <cuda_runtime.h>
 
 #include "tz_abi.h"
@@ -73,12 +75,33 @@ TzSearchCfg MakeCfg(int32_t selector, float c, float c1, float c2, float epsilon
 
 int TreeLeaves(int weighted, int n_emb) { return kFixed + (weighted ? 1 : 0) + n_emb; }
 
+// operand i -> result j on `stream` unless XLA aliased them (same pointer).  Sizes must agree.
+ffi::Error CopyIn(cudaStream_t stream, ffi::RemainingArgs& args, int i, ffi::RemainingRets& rets, int j) {
+  auto src = *args.get<ffi::AnyBuffer>(i);
+  auto dst = **rets.get<ffi::AnyBuffer>(j);
+  if (src.untyped_data() == dst.untyped_data()) return ffi::Error::Success();
+  if (src.size_bytes() != dst.size_bytes()) return ffi::Error(ffi::ErrorCode::kInvalidArgument, "operand / result size mismatch");
+  const cudaError_t e = cudaMemcpyAsync(dst.untyped_data(), src.untyped_data(), src.size_bytes(), cudaMemcpyDeviceToDevice, stream);
+  return e == cudaSuccess ? ffi::Error::Success() : ffi::Error(ffi::ErrorCode::kInternal, cudaGetErrorString(e));
+}
+
+// the first `count` operands into the first `count` results (the tree leaves of a mutating handler)
+ffi::Error CopyInTree(cudaStream_t stream, ffi::RemainingArgs& args, ffi::RemainingRets& rets, int count) {
+  for (int i = 0; i < count; ++i) {
+    auto err = CopyIn(stream, args, i, rets, i);
+    if (err.failure()) return err;
+  }
+  return ffi::Error::Success();
+}
+
 // ---- MCTS.update_root_node + Tree.set_root (mcts.py:363-384, tree.py:135-150) -----------------------------------------
 // args: tree..., root_policy[B,F], root_value[B], root_emb_0..K-1 ; rets: tree... (aliased)
 ffi::Error SetRootImpl(cudaStream_t stream, int32_t weighted, int32_t n_emb, ffi::RemainingArgs args, ffi::RemainingRets rets) {
   const int L = TreeLeaves(weighted, n_emb);
   TzTree t = {};
-  auto err = FillTree([&](int i) { return **rets.get<ffi::AnyBuffer>(i); }, weighted, n_emb, &t);
+  auto err = CopyInTree(stream, args, rets, L);
+  if (err.failure()) return err;
+  err = FillTree([&](int i) { return **rets.get<ffi::AnyBuffer>(i); }, weighted, n_emb, &t);
   if (err.failure()) return err;
   void* emb[TZ_MAX_EMB] = {};
   for (int k = 0; k < n_emb; ++k) emb[k] = args.get<ffi::AnyBuffer>(L + 2 + k)->untyped_data();
@@ -87,17 +110,28 @@ ffi::Error SetRootImpl(cudaStream_t stream, int32_t weighted, int32_t n_emb, ffi
 }
 
 // ---- MCTS.traverse (mcts.py:192-228) + parent-embedding gather (mcts.py:161-164) ---------------------------------------
-// args: tree..., path[B,TZ_PATH_STRIDE] ; rets: parent[B], action[B], path (aliased), emb_parent_0..K-1 [B,...]
+// args: tree..., path[B,TZ_PATH_STRIDE] ; rets: parent[B], action[B], path (aliased), best' [B,N,2] (aliased), sel_state' [B,8]
+// (aliased), emb_parent_0..K-1 [B,...].  The walk fills in unknown best-table entries and a change of selector parameters
+// drops the table, so `best` and `sel_state` are results of this handler too (never written through an operand).
 ffi::Error SelectImpl(cudaStream_t stream, int32_t selector, float c, float c1, float c2, float epsilon, float discount,
                       int32_t weighted, int32_t n_emb, ffi::RemainingArgs args, ffi::RemainingRets rets) {
+  const int L = TreeLeaves(weighted, n_emb);
   TzTree t = {};
   auto err = FillTree([&](int i) { return *args.get<ffi::AnyBuffer>(i); }, weighted, n_emb, &t);
   if (err.failure()) return err;
+  err = CopyIn(stream, args, L, rets, 2);  // path
+  if (err.failure()) return err;
+  err = CopyIn(stream, args, 8, rets, 3);  // best
+  if (err.failure()) return err;
+  err = CopyIn(stream, args, 9, rets, 4);  // sel_state
+  if (err.failure()) return err;
+  t.best = (int32_t*)(*rets.get<ffi::AnyBuffer>(3))->untyped_data();
+  t.sel_state = (int32_t*)(*rets.get<ffi::AnyBuffer>(4))->untyped_data();
   TzWork w = {};
   w.parent = (int32_t*)(*rets.get<ffi::AnyBuffer>(0))->untyped_data();
   w.action = (int32_t*)(*rets.get<ffi::AnyBuffer>(1))->untyped_data();
   w.path = (int32_t*)(*rets.get<ffi::AnyBuffer>(2))->untyped_data();
-  for (int k = 0; k < n_emb; ++k) w.emb_parent[k] = (*rets.get<ffi::AnyBuffer>(3 + k))->untyped_data();
+  for (int k = 0; k < n_emb; ++k) w.emb_parent[k] = (*rets.get<ffi::AnyBuffer>(5 + k))->untyped_data();
   const TzSearchCfg cfg = MakeCfg(selector, c, c1, c2, epsilon, discount, weighted, 1.0f);
   return Status(tz_select(&t, &cfg, &w, stream));
 }
@@ -110,7 +144,9 @@ ffi::Error ExpandImpl(cudaStream_t stream, int32_t selector, float c, float c1, 
                       ffi::RemainingArgs args, ffi::RemainingRets rets) {
   const int L = TreeLeaves(weighted, n_emb);
   TzTree t = {};
-  auto err = FillTree([&](int i) { return **rets.get<ffi::AnyBuffer>(i); }, weighted, n_emb, &t);
+  auto err = CopyInTree(stream, args, rets, fused ? L + 3 : L);  // tree leaves (+ parent / action / path when fused)
+  if (err.failure()) return err;
+  err = FillTree([&](int i) { return **rets.get<ffi::AnyBuffer>(i); }, weighted, n_emb, &t);
   if (err.failure()) return err;
   TzWork w = {};
   // parent / action / path are read (this simulation) and, when fused, rewritten (the next one): aliased in -> out
@@ -148,7 +184,9 @@ ffi::Error RerootImpl(cudaStream_t stream, int32_t persist_tree, int32_t weighte
                       ffi::RemainingRets rets) {
   const int L = TreeLeaves(weighted, n_emb);
   TzTree t = {};
-  auto err = FillTree([&](int i) { return **rets.get<ffi::AnyBuffer>(i); }, weighted, n_emb, &t);
+  auto err = CopyInTree(stream, args, rets, L);
+  if (err.failure()) return err;
+  err = FillTree([&](int i) { return **rets.get<ffi::AnyBuffer>(i); }, weighted, n_emb, &t);
   if (err.failure()) return err;
   return Status(tz_reroot(&t, (const int32_t*)args.get<ffi::AnyBuffer>(L)->untyped_data(),
                           (const uint8_t*)args.get<ffi::AnyBuffer>(L + 1)->untyped_data(), persist_tree, stream));

@@ -41,7 +41,10 @@ class Evaluator:
     def evaluate(self, key, eval_state, env_state, **kwargs) -> EvalOutput:
         raise NotImplementedError()
 
-    def step(self, state, action):  # pylint: disable=unused-argument
+    def step(self, state, action, reset_mask=None, keep_mask=None):  # pylint: disable=unused-argument
+        """evaluator.py:62-72.  `reset_mask` / `keep_mask` (B,) carry the caller's per-env reset-vs-step select
+        (core/common.py:89-94), which the batched `step_env_and_evaluator` folds into this call: envs in `reset_mask`
+        get `reset`, envs in `keep_mask` keep their state.  A stateless evaluator ignores both."""
         return state
 
     def get_value(self, state) -> torch.Tensor:

@@ -44,7 +44,9 @@ TZ_PATH_STRIDE = 66
 def _call(target, out_types, args, aliases=None, **attrs):
     if _NEW_API:
         return _ffi.ffi_call(target, out_types, vmap_method="broadcast_all", input_output_aliases=aliases or {})(*args, **attrs)
-    return _ffi.ffi_call(target, out_types, *args, vectorized=True, **attrs)  # 0.4.35 has no aliasing argument: XLA copies
+    # jax 0.4.35-0.4.37: ffi_call has no aliasing argument, so the result buffers arrive uninitialised; the mutating
+    # handlers copy every operand into its result when the two pointers differ (tz_jax_ffi.cc CopyIn)
+    return _ffi.ffi_call(target, out_types, *args, vectorized=True, **attrs)
 
 
 def aux_init(max_nodes: int, branching_factor: int):
@@ -66,13 +68,17 @@ def _like(xs):
 
 
 def select(tree, aux, path, selector_attrs, weighted=False):
-    """MCTS.traverse (mcts.py:192-228) + parent-embedding gather (mcts.py:161-164).  Un-batched shapes; vmap adds B."""
+    """MCTS.traverse (mcts.py:192-228) + parent-embedding gather (mcts.py:161-164).  Un-batched shapes; vmap adds B.
+    Returns (parent, action, path, (best', sel_state'), parent embeddings): the walk fills in unknown best-table entries, so
+    the caller threads the two returned derived tables back into `aux` (aux = (aux[0], best', sel_state'))."""
     leaves, k = tree_leaves(tree, aux, weighted)
     emb = leaves[-k:] if k else []
     outs = [jax.ShapeDtypeStruct((), jnp.int32), jax.ShapeDtypeStruct((), jnp.int32), jax.ShapeDtypeStruct(path.shape, path.dtype)]
+    outs += _like([aux[1], aux[2]])
     outs += [jax.ShapeDtypeStruct(e.shape[1:], e.dtype) for e in emb]
-    res = _call("TzSelect", outs, leaves + [path], aliases={len(leaves): 2}, weighted=int(weighted), n_emb=k, **selector_attrs)
-    return res[0], res[1], res[2], list(res[3:])
+    res = _call("TzSelect", outs, leaves + [path], aliases={len(leaves): 2, 8: 3, 9: 4}, weighted=int(weighted), n_emb=k,
+                **selector_attrs)
+    return res[0], res[1], res[2], (res[3], res[4]), list(res[5:])
 
 
 def expand_backprop(tree, aux, parent, action, path, policy, value, terminated, new_emb, selector_attrs, weighted=False,

@@ -23,7 +23,7 @@ from torch.utils import _pytree as pytree
 from . import _abi
 from .action_selection import MCTSActionSelector
 from .evaluator import EvalOutput, Evaluator
-from .trees import MCTSTree, Tree, init_tree, _stream_ptr
+from .trees import MCTSTree, Tree, init_tree, _on_device, _same_device, _stream_ptr
 from .types import EnvStepFn, EvalFn, StepMetadata
 
 
@@ -80,12 +80,28 @@ def _scratch(tree: Tree) -> _Scratch:
     return tree._scratch
 
 
-def _rand(key, shape, device) -> torch.Tensor:
-    gen = key if isinstance(key, torch.Generator) else None
+_SEEDED: Dict[Tuple[int, str], torch.Generator] = {}
+
+
+def _generator(key, device) -> Optional[torch.Generator]:
+    """`key` as a torch.Generator on `device`: a Generator is used as is, None means the global RNG, and an int seed maps to
+    ONE generator per (seed, device) that ADVANCES from draw to draw -- re-seeding a fresh generator on every draw would hand
+    every simulation of a search (and every move) the same numbers."""
+    if isinstance(key, torch.Generator):
+        return key
     if isinstance(key, int):
-        gen = torch.Generator(device=device)
-        gen.manual_seed(key)
-    return torch.rand(shape, dtype=torch.float32, device=device, generator=gen)
+        k = (key, str(device))
+        gen = _SEEDED.get(k)
+        if gen is None:
+            gen = torch.Generator(device=device)
+            gen.manual_seed(key)
+            _SEEDED[k] = gen
+        return gen
+    return None
+
+
+def _rand(key, shape, device) -> torch.Tensor:
+    return torch.rand(shape, dtype=torch.float32, device=device, generator=_generator(key, device))
 
 
 class MCTS(Evaluator):
@@ -118,6 +134,8 @@ class MCTS(Evaluator):
         # (programmatic dependent launch).  Legal whenever `leaf_fn` / `env_step_fn` + `eval_fn` enqueue ordinary
         # kernels (see include/tz_abi.h); off by default.
         self.programmatic_launch = False
+        # TzSearchCfg.sim_warps: warps cooperating on one tree in the per-simulation kernel (0 = the library's choice)
+        self.sim_warps = 0
         action_selector.kernel_params()  # raises now if the selector has no device implementation
 
     # ------------------------------------------------------------------------------------------------
@@ -146,7 +164,8 @@ class MCTS(Evaluator):
         inv_t = float(np.float32(1.0 / q_temp)) if q_temp > 0 else 0.0
         return _abi.TzSearchCfg(selector=kp["selector"], c=kp["c"], c1=kp["c1"], c2=kp["c2"], epsilon=kp["epsilon"],
                                 discount=self.discount, weighted=int(self.weighted), inv_q_temperature=inv_t,
-                                fma_backup=int(self.fma_backup), programmatic=self._programmatic_bits())
+                                fma_backup=int(self.fma_backup), programmatic=self._programmatic_bits(),
+                                q_transform=int(kp.get("q_transform", 0)), sim_warps=int(self.sim_warps))
 
     # ------------------------------------------------------------------------------------------------
     def init(self, template_embedding: Any, *args, device=None, **kwargs) -> MCTSTree:  # pylint: disable=arguments-differ
@@ -180,20 +199,21 @@ class MCTS(Evaluator):
         - `root_noise` (B,F) / `uniform01` (B,): the draws `sample_root_action` would take from `key`.
         - `backprop_noise` (S,B,F): WeightedMCTS with q_temperature == 0 only (weighted_mcts.py:123).
         """
-        tree = self.update_root(key, eval_state, env_state, params, root_metadata=root_metadata, **kwargs)
-        lib, cfg, ts = _abi.lib(), self._cfg(), tree.struct()
-        sc = _scratch(tree)
-        stream = _stream_ptr()
-        S = self.num_iterations
-        if S > 0:
-            _abi.check(lib.tz_select(C.byref(ts), C.byref(cfg), C.byref(sc.select_only), stream), "tz_select")
-        for s in range(S):
-            bpn = self._backprop_noise(key, tree, backprop_noise, s)
-            w, keep = self._leaf_work(key, tree, sc, params, env_step_fn, leaf_fn, bpn)
-            fn = lib.tz_expand_backprop_select if s + 1 < S else lib.tz_expand_backprop
-            _abi.check(fn(C.byref(ts), C.byref(cfg), C.byref(w), stream), "tz_expand_backprop")
-            del keep
-        action, policy_weights = self.sample_root_action(key, tree, root_noise=root_noise, uniform01=uniform01)
+        with _on_device(eval_state.device):
+            tree = self.update_root(key, eval_state, env_state, params, root_metadata=root_metadata, **kwargs)
+            lib, cfg, ts = _abi.lib(), self._cfg(), tree.struct()
+            sc = _scratch(tree)
+            stream = _stream_ptr()
+            S = self.num_iterations
+            if S > 0:
+                _abi.check(lib.tz_select(C.byref(ts), C.byref(cfg), C.byref(sc.select_only), stream), "tz_select")
+            for s in range(S):
+                bpn = self._backprop_noise(key, tree, backprop_noise, s)
+                w, keep = self._leaf_work(key, tree, sc, params, env_step_fn, leaf_fn, bpn)
+                fn = lib.tz_expand_backprop_select if s + 1 < S else lib.tz_expand_backprop
+                _abi.check(fn(C.byref(ts), C.byref(cfg), C.byref(w), stream), "tz_expand_backprop")
+                del keep
+            action, policy_weights = self.sample_root_action(key, tree, root_noise=root_noise, uniform01=uniform01)
         return MCTSOutput(eval_state=tree, action=action, policy_weights=policy_weights)
 
     def _backprop_noise(self, key, tree, backprop_noise, s):
@@ -222,6 +242,7 @@ class MCTS(Evaluator):
         if len(leaves) != len(want):
             raise _abi.TzError("new embedding does not match the template embedding's pytree structure")
         emb_new = [l.to(dt).reshape(B, *shape).contiguous() for l, (shape, dt) in zip(leaves, want)]
+        _same_device(tree.device, policy, value, terminated, backprop_noise, *emb_new)
         keep = (policy, value, terminated, emb_new, backprop_noise)
         return sc.work(policy, value, terminated, emb_new, backprop_noise), keep
 
@@ -244,8 +265,10 @@ class MCTS(Evaluator):
         leaves = [l.to(dt).reshape(B, *shape).contiguous()
                   for l, (shape, dt) in zip(pytree.tree_leaves(root_embedding), tree.emb_leaf_shapes())]
         ptrs = (C.c_void_p * max(len(leaves), 1))(*[l.data_ptr() for l in leaves])
-        _abi.check(_abi.lib().tz_set_root(C.byref(tree.struct()), pol.data_ptr(), val.data_ptr(), ptrs, _stream_ptr()),
-                   "tz_set_root")
+        _same_device(tree.device, pol, val, *leaves)
+        with _on_device(tree.device):
+            _abi.check(_abi.lib().tz_set_root(C.byref(tree.struct()), pol.data_ptr(), val.data_ptr(), ptrs, _stream_ptr()),
+                       "tz_set_root")
         return tree
 
     def traverse(self, tree: MCTSTree) -> TraversalState:
@@ -253,8 +276,9 @@ class MCTS(Evaluator):
         tree's scratch (mcts.py:161-164), readable as `parent_embedding(tree)`."""
         sc = _scratch(tree)
         cfg = self._cfg()
-        _abi.check(_abi.lib().tz_select(C.byref(tree.struct()), C.byref(cfg), C.byref(sc.select_only), _stream_ptr()),
-                   "tz_select")
+        with _on_device(tree.device):
+            _abi.check(_abi.lib().tz_select(C.byref(tree.struct()), C.byref(cfg), C.byref(sc.select_only), _stream_ptr()),
+                       "tz_select")
         return TraversalState(parent=sc.parent, action=sc.action)
 
     @staticmethod
@@ -267,9 +291,10 @@ class MCTS(Evaluator):
         self.traverse(tree)
         sc = _scratch(tree)
         cfg = self._cfg()
-        w, keep = self._leaf_work(key, tree, sc, params, env_step_fn, leaf_fn, backprop_noise)
-        _abi.check(_abi.lib().tz_expand_backprop(C.byref(tree.struct()), C.byref(cfg), C.byref(w), _stream_ptr()),
-                   "tz_expand_backprop")
+        with _on_device(tree.device):
+            w, keep = self._leaf_work(key, tree, sc, params, env_step_fn, leaf_fn, backprop_noise)
+            _abi.check(_abi.lib().tz_expand_backprop(C.byref(tree.struct()), C.byref(cfg), C.byref(w), _stream_ptr()),
+                       "tz_expand_backprop")
         del keep
         return tree
 
@@ -289,15 +314,18 @@ class MCTS(Evaluator):
                 uniform01 = _rand(key, (B,), dev)  # consumed by jax.random.choice, mcts.py:294
             uniform01 = uniform01.to(torch.float32).contiguous()
             u_ptr = uniform01.data_ptr()
-        _abi.check(_abi.lib().tz_root_action(C.byref(tree.struct()), float(self.temperature), noise_ptr, u_ptr, None,
-                                             pw.data_ptr(), None, action.data_ptr(), _stream_ptr()), "tz_root_action")
+        _same_device(dev, root_noise if self.temperature == 0 else uniform01)
+        with _on_device(dev):
+            _abi.check(_abi.lib().tz_root_action(C.byref(tree.struct()), float(self.temperature), noise_ptr, u_ptr, None,
+                                                 pw.data_ptr(), None, action.data_ptr(), _stream_ptr()), "tz_root_action")
         return action, pw
 
     def root_visits(self, tree: MCTSTree) -> torch.Tensor:
         """tree.get_child_data('n', ROOT) (mcts.py:276) as one kernel: (B,F) int32."""
         visits = torch.empty((tree.batch_size, tree.branching_factor), dtype=torch.int32, device=tree.device)
-        _abi.check(_abi.lib().tz_root_action(C.byref(tree.struct()), 1.0, None, None, visits.data_ptr(), None, None, None,
-                                             _stream_ptr()), "tz_root_action")
+        with _on_device(tree.device):
+            _abi.check(_abi.lib().tz_root_action(C.byref(tree.struct()), 1.0, None, None, visits.data_ptr(), None, None, None,
+                                                 _stream_ptr()), "tz_root_action")
         return visits
 
     # ------------------------------------------------------------------------------------------------
@@ -306,8 +334,11 @@ class MCTS(Evaluator):
         flags = None
         if mask is not None:
             flags = torch.where(mask.bool(), 1, 2).to(torch.uint8).contiguous()  # 1 = reset, 2 = leave untouched
-        _abi.check(_abi.lib().tz_reroot(C.byref(state.struct()), None, None if flags is None else flags.data_ptr(),
-                                        0 if flags is None else 1, _stream_ptr()), "tz_reroot")
+            _same_device(state.device, flags)
+        # persist_tree = 0: no tree is re-rooted here, so no action is needed (flag 2 returns before the reset test)
+        with _on_device(state.device):
+            _abi.check(_abi.lib().tz_reroot(C.byref(state.struct()), None, None if flags is None else flags.data_ptr(), 0,
+                                            _stream_ptr()), "tz_reroot")
         return state
 
     def step(self, state: MCTSTree, action: torch.Tensor, reset_mask: Optional[torch.Tensor] = None,
@@ -323,6 +354,8 @@ class MCTS(Evaluator):
                 flags = torch.where(keep_mask.bool(), 2, flags.int()).to(torch.uint8)
             flags = flags.contiguous()
         act = action.to(torch.int32).contiguous()
-        _abi.check(_abi.lib().tz_reroot(C.byref(state.struct()), act.data_ptr(), None if flags is None else flags.data_ptr(),
-                                        1 if self.persist_tree else 0, _stream_ptr()), "tz_reroot")
+        _same_device(state.device, act, flags)
+        with _on_device(state.device):
+            _abi.check(_abi.lib().tz_reroot(C.byref(state.struct()), act.data_ptr(), None if flags is None else flags.data_ptr(),
+                                            1 if self.persist_tree else 0, _stream_ptr()), "tz_reroot")
         return state

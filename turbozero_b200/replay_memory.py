@@ -19,7 +19,7 @@ import torch
 from torch.utils import _pytree as pytree
 
 from . import _abi
-from .trees import _stream_ptr
+from .trees import _on_device, _stream_ptr
 
 
 @dataclass(frozen=True)
@@ -124,10 +124,11 @@ class EpisodeReplayBuffer:
         rew = None if reward is None else reward.to(torch.float32).contiguous()
         term = None if terminated is None else terminated.to(torch.uint8).contiguous()
         trunc = None if truncated is None else truncated.to(torch.uint8).contiguous()
-        _abi.check(_abi.lib().tz_replay_collect(
-            C.byref(state._struct), len(experiences), arr, None if rew is None else rew.data_ptr(),
-            None if term is None else term.data_ptr(), None if trunc is None else trunc.data_ptr(), _stream_ptr()),
-            "tz_replay_collect")
+        with _on_device(state.populated.device):
+            _abi.check(_abi.lib().tz_replay_collect(
+                C.byref(state._struct), len(experiences), arr, None if rew is None else rew.data_ptr(),
+                None if term is None else term.data_ptr(), None if trunc is None else trunc.data_ptr(), _stream_ptr()),
+                "tz_replay_collect")
         return state
 
     def add_experience(self, state: ReplayBufferState, experience) -> ReplayBufferState:
@@ -157,11 +158,12 @@ class EpisodeReplayBuffer:
         n_valid = torch.empty((1,), dtype=torch.int32, device=gumbel.device)
         g = gumbel.to(torch.float32).contiguous()
         lib = _abi.lib()
-        _abi.check(lib.tz_replay_count_valid(C.byref(state._struct), n_valid.data_ptr(), _stream_ptr()), "tz_replay_count_valid")
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(n_valid, op=dist.ReduceOp.SUM, group=group)
-        _abi.check(lib.tz_replay_sample_scores(C.byref(state._struct), g.data_ptr(), n_valid.data_ptr(), scores.data_ptr(),
-                                               _stream_ptr()), "tz_replay_sample_scores")
+        with _on_device(state.populated.device):
+            _abi.check(lib.tz_replay_count_valid(C.byref(state._struct), n_valid.data_ptr(), _stream_ptr()), "tz_replay_count_valid")
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                dist.all_reduce(n_valid, op=dist.ReduceOp.SUM, group=group)
+            _abi.check(lib.tz_replay_sample_scores(C.byref(state._struct), g.data_ptr(), n_valid.data_ptr(), scores.data_ptr(),
+                                                   _stream_ptr()), "tz_replay_sample_scores")
         return scores
 
     def gather(self, state: ReplayBufferState, flat_index: torch.Tensor):
@@ -170,7 +172,8 @@ class EpisodeReplayBuffer:
         n = int(idx.numel())
         outs = [torch.empty((n, *t.shape[2:]), dtype=t.dtype, device=t.device) for t in state._leaves]
         ptrs = (C.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
-        _abi.check(_abi.lib().tz_replay_gather(C.byref(state._struct), idx.data_ptr(), n, ptrs, _stream_ptr()), "tz_replay_gather")
+        with _on_device(state.populated.device):
+            _abi.check(_abi.lib().tz_replay_gather(C.byref(state._struct), idx.data_ptr(), n, ptrs, _stream_ptr()), "tz_replay_gather")
         if hasattr(state.buffer, "__dataclass_fields__"):
             names = [f.name for f in sorted(fields(state.buffer), key=lambda f: f.name)]
             return type(state.buffer)(**dict(zip(names, outs)))
@@ -185,10 +188,18 @@ class EpisodeReplayBuffer:
         dev = state.populated.device
         n = state.populated.numel()
         if gumbel is None:
-            gen = key if isinstance(key, torch.Generator) else None
-            if isinstance(key, int):
-                gen = torch.Generator(device=dev)
-                gen.manual_seed(key)
+            import torch.distributed as dist_
+
+            rank_ = dist_.get_rank(group) if (dist_.is_available() and dist_.is_initialized()) else 0
+            # every rank scores ITS OWN slots: the noise streams of the ranks must differ, or slot i gets the same key on
+            # every rank and the draw is no longer uniform over the global buffer.  An int seed is folded with the rank; a
+            # Generator is the caller's responsibility (seed it per rank).
+            from .mcts import _generator
+
+            if isinstance(key, torch.Generator):
+                gen = key
+            else:  # int seed, or None = a private stream derived from the process's global seed; both advance per draw
+                gen = _generator(int(key if isinstance(key, int) else torch.initial_seed()) + 1000003 * rank_, dev)
             u = torch.rand((n,), dtype=torch.float32, device=dev, generator=gen).clamp_(min=torch.finfo(torch.float32).tiny)
             gumbel = -torch.log(-torch.log(u))
         scores = self.sample_scores(state, gumbel, group)

@@ -40,8 +40,37 @@ class MCTSNode:
 WeightedMCTSNode = MCTSNode
 
 
-def _stream_ptr() -> int:
-    return torch.cuda.current_stream().cuda_stream
+def _stream_ptr(device=None) -> int:
+    """The current CUDA stream of `device` (default: the current device) as the raw cudaStream_t the C-ABI takes."""
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class _on_device:
+    """Context for one or more C-ABI calls on the tensors of `device`: kernels launch on -- and per-device function
+    attributes are set on -- the calling thread's CURRENT device, so a tree that lives elsewhere must make its device
+    current first (a process that drives several GPUs, or a tree not on the current device).  Free when it already is."""
+    __slots__ = ("_ctx",)
+
+    def __init__(self, device: torch.device):
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        self._ctx = None if idx == torch.cuda.current_device() else torch.cuda.device(idx)
+
+    def __enter__(self):
+        if self._ctx is not None:
+            self._ctx.__enter__()
+        return self
+
+    def __exit__(self, *exc):
+        if self._ctx is not None:
+            return self._ctx.__exit__(*exc)
+        return False
+
+
+def _same_device(device: torch.device, *tensors) -> None:
+    for t in tensors:
+        if t is not None and t.device != device:
+            raise _abi.TzError(f"tensor on {t.device} passed to a tree batch on {device}: all inputs of a call must live "
+                               "on the tree's device")
 
 
 @dataclass
@@ -141,7 +170,8 @@ class Tree:
     # --- mutating ops (in place, stream-ordered, no sync) ---
     def reset(self) -> "Tree":
         """tree.py:272-278 for the whole batch (every row rewritten)."""
-        _abi.check(_abi.lib().tz_tree_init(C.byref(self.struct()), _stream_ptr()), "tz_tree_init")
+        with _on_device(self.device):
+            _abi.check(_abi.lib().tz_tree_init(C.byref(self.struct()), _stream_ptr()), "tz_tree_init")
         return self
 
     def get_subtree(self, subtree_index: torch.Tensor, reset_mask: Optional[torch.Tensor] = None) -> "Tree":
@@ -149,14 +179,17 @@ class Tree:
         trees whose `reset_mask` is set are reset (tree.py:272-278) instead."""
         act = subtree_index.to(torch.int32).contiguous()
         rm = None if reset_mask is None else reset_mask.to(torch.uint8).contiguous()
-        _abi.check(_abi.lib().tz_reroot(C.byref(self.struct()), act.data_ptr(), None if rm is None else rm.data_ptr(), 1,
-                                        _stream_ptr()), "tz_reroot")
+        _same_device(self.device, act, rm)
+        with _on_device(self.device):
+            _abi.check(_abi.lib().tz_reroot(C.byref(self.struct()), act.data_ptr(), None if rm is None else rm.data_ptr(), 1,
+                                            _stream_ptr()), "tz_reroot")
         return self
 
     def rebuild_child_stats(self) -> "Tree":
         """Recomputes the derived child_stats table from edge_map / p / q / n / terminated and forgets the cached selector
         decisions (needed only after those leaves were written from outside the kernels)."""
-        _abi.check(_abi.lib().tz_rebuild_child_stats(C.byref(self.struct()), _stream_ptr()), "tz_rebuild_child_stats")
+        with _on_device(self.device):
+            _abi.check(_abi.lib().tz_rebuild_child_stats(C.byref(self.struct()), _stream_ptr()), "tz_rebuild_child_stats")
         return self
 
     def slice(self, start: int, stop: int) -> "Tree":
