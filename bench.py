@@ -1,24 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- MCTS simulations/sec of the batched search hot path (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2] [--named cfg3,cfg4] [--impl reference]
 
 A STEP is one self-play move of every env on this rank: root evaluation + set_root, S simulations
 (select -> leaf -> expand+backprop), root-action sampling, env step, and subtree re-rooting (or reset where the
 episode ended) -- i.e. `step_env_and_evaluator` of the reference (core/common.py:32-103) with the user's pgx env and
 network replaced by the synthetic stand-in (pgx / JAX are not installable here).
 
-Default workload = BASELINE.json configs[1]: connect_four shape, 1024 envs x 128 simulations, max_nodes 256, subtree
+Headline workload = BASELINE.json configs[1]: connect_four shape, 1024 envs x 128 simulations, max_nodes 256, subtree
 persistence on, one B200.  With --gpus N every rank owns its own 1024 envs (independent tree batches, no collective
 in the search) => weak scaling; `value` is the whole-job aggregate.
 
-Legs of the default arm (all in one JSON line):
+The configs BASELINE.json names for N > 1 GPUs are measured in the same run and reported under `config.named`
+(each with its own value / e2e / ms_per_step / roofline):
+  N = 2, 4, 8   configs[2]  othello 8x8, 4096 envs (strong-scaled: 4096 / N per GPU) x 200 sims, WeightedMCTS backup
+  N = 8         configs[3]  go_9x9, 8192 envs (1024 per GPU) x 800 sims
+  N = 8         configs[4]  2048, 16384 envs (2048 per GPU) x 100 sims, discount +1, with the replay-buffer update in the
+                            step, ONE cross-rank replay sample (NCCL all-gather / all-reduce) and the gradient-mean
+                            all-reduce of a parameter-sized buffer per step (core/training/train.py:393-437)
+`--named cfgX,...` forces named legs at any N (single-GPU shares of the configs; used for development runs).
+
+Legs of every workload (all in one JSON line):
   value        device-resident inputs, one CUDA-graph replay per step, per-step CUDA events, L2 flushed between steps
-  e2e          the public Python API (MCTS.evaluate + MCTS.step, captured by the user in a CUDA graph) with per-step
-               H2D copies of the step's random inputs from pinned memory and a D2H read of actions + policy weights
-  roofline     the per-simulation kernel (k_sim: expand+backprop+select) timed by CUDA events recorded around every
-               launch on the launching stream; achieved = algorithmic bytes / duration  vs measured HBM peak
-  cpu_baseline the CPU oracle (C restatement, OpenMP over trees) on a bounded sample of the same workload (rank 0, N=1)
+  e2e          the public Python API (step_env_and_evaluator = MCTS.evaluate + MCTS.step, captured by the user in a CUDA
+               graph) with per-step H2D copies of the step's random inputs from pinned memory and a D2H read of
+               actions + policy weights
+  roofline     the per-simulation kernel (expand+backprop+select) timed INSIDE the step it describes: the same graph
+               instantiation (programmatic launches included) replayed with the launch timeline on (TzWork.timeline:
+               %globaltimer at first warp in / last warp out of every launch); achieved = algorithmic bytes / that
+               duration vs the measured HBM peak.  launches x avg duration <= ms_per_step is asserted.
+  cpu_baseline the CPU oracle (C restatement, OpenMP over trees) on a bounded sample of the same workload (rank 0,
+               N = 1), plus the literal per-tree NumPy restatement (the masked-dataflow oracle) on a smaller sample
 
 `--impl reference`: the reference's algorithm on the host CPU only (the oracle port; the real reference needs JAX,
 which is absent), all host threads, same config / metric.
@@ -44,18 +57,21 @@ import numpy as np  # noqa: E402
 METRIC = "mcts_simulations_per_sec"
 UNIT = "simulations/s"
 
-# name -> (synthetic game shape, envs per GPU, simulations, max_nodes, weighted, discount, description)
+# name -> (synthetic game shape, envs per GPU at the config's GPU count, simulations, max_nodes, weighted, discount, description)
 # Programmatic dependent launches (TzSearchCfg.programmatic) are on by default except for the go_9x9 shape, whose leaf
 # stand-in runs long enough that a waiting search grid costs more than the overlap saves (profiles/r1h_pdl_modes.log).
 NO_PDL_BY_DEFAULT = {"cfg4"}
 REPLAY_CAPACITY = 256  # slots per env of the episode replay buffer in the cfg5 step
+TRAIN_BATCH = 1024     # rows of the cross-rank replay sample per step (cfg5, N > 1)
+GRAD_FLOATS = 2 << 20  # parameter-sized buffer of the gradient-mean all-reduce (cfg5, N > 1): 2 Mi fp32 = 8 MiB
 WORKLOADS = {
     "cfg1": ("tic_tac_toe", 32, 64, 128, False, -1.0, "tic_tac_toe 32 envs x 64 sims (configs[0])"),
     "cfg2": ("connect_four", 1024, 128, 256, False, -1.0, "connect_four 1024 envs x 128 sims, persist_tree (configs[1])"),
-    "cfg3": ("othello", 512, 200, 400, True, -1.0, "othello 4096 envs / 8 GPUs x 200 sims, WeightedMCTS (configs[2])"),
+    "cfg3": ("othello", 512, 200, 400, True, -1.0, "othello 4096 envs x 200 sims, WeightedMCTS (configs[2])"),
     "cfg4": ("go_9x9", 1024, 800, 1600, False, -1.0, "go_9x9 8192 envs / 8 GPUs x 800 sims (configs[3])"),
-    "cfg5": ("2048", 2048, 100, 200, False, 1.0, "2048 16384 envs / 8 GPUs x 100 sims, discount +1 (configs[4])"),
+    "cfg5": ("2048", 2048, 100, 200, False, 1.0, "2048 16384 envs / 8 GPUs x 100 sims, discount +1, replay memory (configs[4])"),
 }
+CFG3_TOTAL_ENVS = 4096
 
 
 def parse_args():
@@ -65,11 +81,13 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="cfg2", choices=list(WORKLOADS))
-    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU")
+    ap.add_argument("--named", default=None, help="comma-separated workloads to add under config.named (default: by --gpus)")
+    ap.add_argument("--envs", type=int, default=0, help="override envs per GPU of the headline workload")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="ordinary stream-ordered launches (TzSearchCfg.programmatic = 0)")
     ap.add_argument("--pdl", action="store_true", help="force programmatic dependent launches on")
+    ap.add_argument("--sim-warps", type=int, default=0, help="TzSearchCfg.sim_warps (0 = library's choice)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
     ap.add_argument("--skip-roofline", action="store_true")
@@ -174,6 +192,32 @@ def cpu_moves(CO, cg, cfg, t, S, moves, dn, rn, u, core, payload, episode, nthre
     return time.perf_counter() - t0
 
 
+def numpy_oracle_baseline(wl, seed, seconds=6.0):
+    """The literal per-tree NumPy restatement (oracle/mcts_numpy.py: the reference's gathers / scatters / where-selects /
+    N-1 label rounds, one env at a time as vmap's per-example program) on a small sample of the same workload: BASELINE.md
+    section 3's `oracle-batched` stand-in for the reference's vmapped JAX-CPU path.  One thread."""
+    from helpers import Schedule, run_numpy
+    from oracle import synth_numpy as SN
+
+    name, _, S, N, weighted, discount, _ = WORKLOADS[wl]
+    g = SN.make_game(name, seed)
+    envs, spent, sims = 1, 0.0, 0
+    while True:
+        s = Schedule(game=g, B=envs, N=N, S=S, moves=1, temperature=1.0, weighted=weighted, discount=discount, seed=seed)
+        t0 = time.perf_counter()
+        run_numpy(s)
+        dt = time.perf_counter() - t0
+        spent += dt
+        sims += envs * S
+        last, last_envs = envs * S / dt, envs
+        if spent + 2.2 * dt > seconds or envs >= 64:  # the next (doubled) sample would overrun the budget
+            break
+        envs *= 2
+    return {"value": last, "unit": UNIT, "cores": 1, "kind": "port-numpy",
+            "sample": f"one move of {last_envs} envs x {S} sims ({dt:.1f} s; {sims} simulations in {spent:.1f} s in all), "
+                      "oracle/mcts_numpy.py per tree, single thread"}
+
+
 def run_reference(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -201,7 +245,7 @@ def run_reference(args, out):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
-        "config": {"workload": desc, "envs": B, "simulations": S, "max_nodes": N, "branching_factor": g.F,
+        "config": {"workload": desc, "envs_per_gpu": B, "envs": B, "simulations": S, "max_nodes": N, "branching_factor": g.F,
                    "embedding_bytes": g.payload_bytes + 16, "note": "reference algorithm on host CPU via the oracle port "
                    "(oracle/tz_oracle.c); the reference itself needs JAX, which is not installable in this image"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -214,47 +258,37 @@ def run_reference(args, out):
 # ------------------------------------------------------------------------------------------------------------------
 # native arm
 # ------------------------------------------------------------------------------------------------------------------
-def run_native(args, out):
+class Ctx:
+    pass
+
+
+def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
+    """All legs of one workload on this rank's share of `B` envs.  Returns a dict (identical on every rank where it
+    matters: times are max-reduced over ranks)."""
     import torch
     import torch.distributed as dist
 
-    import turbozero_b200 as tz
-    from turbozero_b200 import _abi
+    tz, _abi, lib, slib, dev, rank, world, args = cx.tz, cx._abi, cx.lib, cx.slib, cx.dev, cx.rank, cx.world, cx.args
     from turbozero_b200.common import step_env_and_evaluator
     from turbozero_b200.synthetic import SyntheticEnv, SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
 
-    if not torch.cuda.is_available():
-        raise RuntimeError("bench.py (native arm) needs a CUDA device; there is no CPU fallback for the search kernels")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    name, _, S, N, weighted, discount, desc = WORKLOADS[wl]
+    seed = 1000 + rank
+    game = SyntheticGame.named(name, seed)
+    F, E = game.F, game.emb_bytes
+    base = tz.WeightedMCTS if weighted else tz.MCTS
+    with_replay = wl == "cfg5"  # "full self-play + replay memory" (BASELINE.json configs[4])
+    with_nccl = with_replay and world > 1
 
     def barrier():
         if world > 1:
             dist.barrier()
 
-    wl = args.workload
-    name, B0, S, N, weighted, discount, desc = WORKLOADS[wl]
-    B = args.envs or B0
-    K, W = args.steps, max(args.warmup, 3)  # timing rule: never fewer than 3 warm-up steps
-    seed = 1000 + rank
-    game = SyntheticGame.named(name, seed)
-    F, E = game.F, game.emb_bytes
-    base = tz.WeightedMCTS if weighted else tz.MCTS
-
-    use_pdl = args.pdl or (not args.no_pdl and wl not in NO_PDL_BY_DEFAULT)
-    with_replay = wl == "cfg5"  # "full self-play + replay memory" (BASELINE.json configs[4])
-
-    def new_eval(programmatic=None):
-        return make_synthetic_evaluator(base, game, action_selector=tz.PUCTSelector(), max_nodes=N, num_iterations=S,
-                                        discount=discount, temperature=1.0,
-                                        programmatic=use_pdl if programmatic is None else programmatic)
-
-    lib, slib = _abi.lib(), _abi.synth_lib()
+    def new_eval(programmatic):
+        ev = make_synthetic_evaluator(base, game, action_selector=tz.PUCTSelector(), max_nodes=N, num_iterations=S,
+                                      discount=discount, temperature=1.0, programmatic=programmatic)
+        ev.sim_warps = args.sim_warps
+        return ev
 
     def launches():
         return lib.tz_launch_count() + slib.tz_synth_launch_count()
@@ -262,16 +296,15 @@ def run_native(args, out):
     rng = np.random.default_rng(seed)
     total = W + K
     dn_h, rn_h, u_h = host_inputs(rng, total, B, F)
-    flush_buf = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=dev)
 
     def flush():
-        if flush_buf is not None:
-            flush_buf.fill_(1)
+        if cx.flush_buf is not None:
+            cx.flush_buf.fill_(1)
 
-    # ---------------- leg 1: device-resident inputs, whole move in the C-ABI (tz_search + leaf callback) ----------
     dn_d, rn_d, u_d = (torch.from_numpy(x).to(dev) for x in (dn_h, rn_h, u_h))
 
-    def timed_moves(programmatic, with_clocks):
+    # ---------------- leg 1: device-resident inputs, whole move in the C-ABI (tz_search + leaf callback) ----------
+    def timed_moves(programmatic, with_clocks, keep):
         """W warm-up + K timed self-play moves (one CUDA-graph replay each, per-step events, L2 flushed in between)."""
         slib.tz_synth_set_programmatic(1 if programmatic else 0)
         ev_ = new_eval(programmatic)
@@ -283,6 +316,8 @@ def run_native(args, out):
             sp_.uniform01.copy_(u_d[i], non_blocking=True)
 
         one_move = sp_.move
+        after_step = None
+        extra = {}
         if with_replay:
             # configs[4] names "full self-play + replay memory": the collection step's buffer update (Trainer.collect,
             # core/training/train.py:300-340 -> tz_replay_collect) runs inside the step, fed from static buffers
@@ -304,12 +339,27 @@ def run_native(args, out):
                                         observation_nn=x_obs, cur_player_id=x_player)
                 rb.collect_update(rstate, [exp], x_rew, sp_.reset_flag, x_trunc)
 
+            if with_nccl:
+                # the training step's two exchange steps, once per move, OUTSIDE the search (north star: "NCCL only for the
+                # existing gradient mean and replay-memory gather"): one sample of TRAIN_BATCH rows over the buffers of all
+                # ranks (replay_memory.py:137-183 / train.py:435-437: all-reduce of the valid count, all-gather of every
+                # rank's candidates, all-reduce of the owners' rows) and the gradient mean (train.py:393,397) of a
+                # parameter-sized buffer.  Enqueued eagerly after the graph replay.
+                grads = torch.zeros((GRAD_FLOATS,), dtype=torch.float32, device=dev)
+                extra["nccl"] = {"replay_sample_rows": TRAIN_BATCH, "grad_allreduce_bytes": GRAD_FLOATS * 4}
+
+                def after_step():
+                    rb.sample(rstate, 17, TRAIN_BATCH)
+                    dist.all_reduce(grads, op=dist.ReduceOp.AVG)
+
         l0 = launches()
         one_move()  # un-captured first move: loads modules, sizes caches
+        if after_step:
+            after_step()
         torch.cuda.synchronize()
         per_move = launches() - l0
         if args.no_graph:
-            step = one_move
+            replay = one_move
         else:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -318,7 +368,13 @@ def run_native(args, out):
                 with torch.cuda.graph(cg, stream=side):
                     one_move()
             torch.cuda.current_stream().wait_stream(side)
-            step = cg.replay
+            replay = cg.replay
+
+        def step():
+            replay()
+            if after_step:
+                after_step()
+
         for i in range(W):
             load_inputs_(i)
             step()
@@ -327,7 +383,7 @@ def run_native(args, out):
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
         barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local) if (rank == 0 and with_clocks) else None
+        sampler = ClockSampler(cx.local) if (rank == 0 and with_clocks) else None
         t_wall0 = time.perf_counter()
         for i in range(K):
             load_inputs_(W + i)
@@ -346,83 +402,118 @@ def run_native(args, out):
                 step()
                 torch.cuda.synchronize()
         clocks_ = sampler.stop() if sampler else None
-        ms = sum(a_.elapsed_time(b_) for a_, b_ in evs)
+        per_step = [a_.elapsed_time(b_) for a_, b_ in evs]
         d_st = sp_.tree.stats.sum(0).cpu().numpy().astype(np.int64) - st0
-        t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t_ms = torch.tensor([sum(per_step), -min(per_step), max(per_step), statistics.median(per_step)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        return float(t_ms.item()), float(d_st[0]) / max(float(d_st[1]), 1.0), per_move, clocks_, sp_, load_inputs_
+        res = {"ms_total": float(t_ms[0]), "ms_min": -float(t_ms[1]), "ms_max": float(t_ms[2]), "ms_median": float(t_ms[3]),
+               "levels_per_sim": float(d_st[0]) / max(float(d_st[1]), 1.0), "launches_per_move": int(per_move), "clocks": clocks_,
+               "extra": extra}
+        if keep:
+            res["sp"], res["load_inputs"], res["one_move"] = sp_, load_inputs_, one_move
+        return res
 
-    other_ms = None
-    if use_pdl and not args.skip_roofline:  # the same moves with ordinary launches, for the record (config.ordinary_launches)
-        other_ms = timed_moves(False, False)[0]
-    max_ms, levels_per_sim, launches_per_move, clocks, sp, load_inputs = timed_moves(use_pdl, True)
-    value = world * B * S * K / (max_ms * 1e-3)
+    total_envs = strong_total if strong_total else B * world
+    other = None
+    if use_pdl and "ordinary" in legs:  # the same moves with ordinary launches: what a user's framework kernels get by default
+        other = timed_moves(False, False, False)
+    main = timed_moves(use_pdl, True, True)
+    sp, load_inputs, one_move = main.pop("sp"), main.pop("load_inputs"), main.pop("one_move")
+    ms_per_step = main["ms_total"] / K
+    value = total_envs * S * K / (main["ms_total"] * 1e-3)
 
-    # ---------------- leg 2: roofline of the dominant kernel (k_sim), CUDA events around every launch --------------
+    # ---------------- leg 2: roofline of the per-simulation kernel, timed inside the step it describes ---------------
     roofline = None
-    if not args.skip_roofline:
+    if "roofline" in legs:
         peak, peak_src = measured_peaks()
         moves_r = 3
-        if slib.tz_synth_timed_begin(S) != 0:
-            raise RuntimeError("tz_synth_timed_begin failed")
-        saved = sp._cb
-        saved_prog = int(sp.cfg.programmatic)  # timed alone => the ordinary-launch form of the kernel (events between the
-        sp.cfg.programmatic = 0                # launches would serialise a programmatic pair anyway)
-        slib.tz_synth_set_programmatic(0)
-        sp._cb = (C.cast(slib.tz_synth_leaf_cb_timed, C.c_void_p), saved[1], saved[2])
-        ms_buf = (C.c_float * (S - 1))()
-        leaf_buf = (C.c_float * S)()
-        durs, leaf_durs = [], []
+        # the SAME instantiation the headline runs (programmatic or not, inside a graph), captured once more with the launch
+        # timeline on: every search launch and every leaf launch records first-warp-in / inputs-ready / last-warp-out
+        sp.timeline_begin()
+        mark = sp.timeline_mark()
+        if args.no_graph:
+            replay_tl = one_move
+        else:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            cg_tl = torch.cuda.CUDAGraph()
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(cg_tl, stream=side):
+                    one_move()
+            torch.cuda.current_stream().wait_stream(side)
+            replay_tl = cg_tl.replay
+        n_search, n_leaf = S + 1, S  # select, S-1 fused launches, expand-only; S leaf launches
+        resident, after_inputs, leaf_exec, gap_ls, gap_sl, period = [], [], [], [], [], []
         st0 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
-        blocker = flush_buf if flush_buf is not None else torch.empty(512 << 20, dtype=torch.uint8, device=dev)
         for m in range(moves_r):
             load_inputs(W + m)
-            for _ in range(24):  # ~2 ms of queued fills: the whole move is enqueued before the GPU reaches it,
-                blocker.fill_(m)  # so the events measure device time, not host enqueue gaps (and L2 starts cold)
-            sp.move()
+            sp.timeline_clear()
+            if args.no_graph:
+                mark = sp.timeline_mark()
+            flush()
+            replay_tl()
             torch.cuda.synchronize()
-            if slib.tz_synth_timed_collect(ms_buf, leaf_buf) != 0:
-                raise RuntimeError("tz_synth_timed_collect failed")
-            durs.extend(ms_buf)  # fused launches: expand+backprop of sim s, select of sim s+1
-            leaf_durs.extend(leaf_buf)
-        sp._cb = saved
-        # the re-root launch of three more moves, timed the same way (the streaming kernel of the path)
+            ts, tl = sp.timeline_read(mark, n_search, n_leaf)
+            # fused launch j (1 <= j <= S-1) sits between leaf j-1 and leaf j
+            for j in range(1, S):
+                s_in, s_rdy, s_out = (int(x) for x in ts[j])
+                l_in, l_rdy, l_out = (int(x) for x in tl[j - 1])
+                n_in, n_rdy, n_out = (int(x) for x in tl[j])
+                if min(s_in, l_in, n_in) < 0 or s_out == 0 or l_out == 0 or n_out == 0:
+                    continue  # a row that was not written (cannot happen; guards the arithmetic)
+                resident.append(s_out - s_in)
+                after_inputs.append(s_out - max(s_rdy, l_out) if s_rdy else s_out - max(s_in, l_out))
+                leaf_exec.append(l_out - l_rdy)
+                gap_ls.append(max(s_rdy, s_in) - l_out if s_rdy else s_in - l_out)
+                gap_sl.append(n_rdy - s_out)
+                period.append(n_rdy - l_rdy)
+        sp.timeline_end()
+        st1 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
+        us = lambda xs: (sum(xs) / max(len(xs), 1)) * 1e-3
+        dur_us = us(resident)
+        dl, ds = int(st1[0] - st0[0]), int(st1[1] - st0[1])
+        bytes_total = algorithmic_bytes(dl, ds, F, E, weighted)
+        bytes_per_launch = bytes_total / max(ds // B, 1)
+        achieved = bytes_per_launch / (dur_us * 1e-6) / 1e9 if dur_us > 0 else 0.0
+        fits = (S - 1) * dur_us * 1e-3 <= ms_per_step * 1.02
+        assert fits or args.no_graph, (f"roofline leg inconsistent: {S - 1} launches x {dur_us:.2f} us = {(S - 1) * dur_us * 1e-3:.3f} ms "
+                                       f"exceeds ms_per_step {ms_per_step:.3f}")
+        traffic = None
+        if wl == "cfg2" and B == WORKLOADS["cfg2"][1]:  # per-launch DRAM bytes of this kernel on this shape, from the committed ncu capture
+            try:
+                with open(os.path.join(ROOT, "profiles", "ksim_traffic.json")) as f:
+                    traffic = float(json.load(f)["traffic_bytes_per_launch"])
+            except Exception:
+                traffic = None
+        roofline = {"bound": "hbm", "kernel": "k_sim (expand+backprop of simulation i fused with select of i+1): the instantiation "
+                    "the headline step runs, timed inside a replay of that step (first warp in -> last warp out, %globaltimer)",
+                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                    "traffic_source": "profiles/ksim_traffic.json (ncu --set full, cold L2)" if traffic else None,
+                    "peak_source": peak_src, "avg_launch_us": dur_us, "median_launch_us": statistics.median(resident) * 1e-3 if resident else None,
+                    "launches_timed": len(resident), "launches_per_step": S - 1,
+                    "launches_x_avg_ms": (S - 1) * dur_us * 1e-3, "fits_in_ms_per_step": bool(fits),
+                    "algorithmic_bytes_per_launch": bytes_per_launch, "levels_per_sim": dl / max(ds, 1),
+                    "per_simulation_us": {"period": us(period), "leaf_stand_in_exec": us(leaf_exec),
+                                          "leaf_out_to_search_inputs_ready": us(gap_ls), "search_after_inputs_ready": us(after_inputs),
+                                          "search_out_to_next_leaf_running": us(gap_sl)},
+                    "note": "a launch moves a few MB for ~1 K trees: it is bound by the dependent chain of one warp (or CTA) per "
+                            "tree and by the two grid-completion -> dependent-start hand-overs per simulation, not by bandwidth; "
+                            "see DESIGN.md section 3"}
+        # the re-root launch of three more moves, timed by events around the launch (eager moves: the events bracket one kernel)
         rr_ms, rr_st0 = [], sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
+        blocker = cx.flush_buf if cx.flush_buf is not None else torch.empty(64 << 20, dtype=torch.uint8, device=dev)
         for m in range(moves_r):
             load_inputs(W + m)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             sp.reroot_events = (e0, e1)
-            for _ in range(24):
+            for _ in range(4):  # queued fills: the move is enqueued before the GPU reaches it (no host gaps inside)
                 blocker.fill_(m)
             sp.move()
             torch.cuda.synchronize()
             rr_ms.append(e0.elapsed_time(e1))
         sp.reroot_events = None
         rr_st = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64) - rr_st0
-        sp.cfg.programmatic = saved_prog
-        slib.tz_synth_set_programmatic(1 if use_pdl else 0)
-        st1 = sp.tree.stats.sum(0).cpu().numpy().astype(np.int64)
-        dur_ms = sum(durs) / len(durs)
-        dl, ds = int(st1[0] - st0[0]), int(st1[1] - st0[1])
-        bytes_total = algorithmic_bytes(dl, ds, F, E, weighted)
-        bytes_per_launch = bytes_total / max(ds // B, 1)
-        achieved = bytes_per_launch / (dur_ms * 1e-3) / 1e9
-        traffic = None
-        if wl == "cfg2" and B == B0:  # per-launch DRAM bytes of this kernel on this shape, from the committed ncu capture
-            try:
-                with open(os.path.join(ROOT, "profiles", "ksim_traffic.json")) as f:
-                    traffic = float(json.load(f)["traffic_bytes_per_launch"])
-            except Exception:
-                traffic = None
-        roofline = {"bound": "hbm", "kernel": "k_sim (expand+backprop of simulation i fused with select of i+1), ordinary-launch form, timed alone",
-                    "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                    "traffic_source": "profiles/ksim_traffic.json (ncu --set full, cold L2)" if traffic else None,
-                    "peak_source": peak_src, "avg_launch_us": dur_ms * 1e3, "median_launch_us": statistics.median(durs) * 1e3,
-                    "avg_leaf_stand_in_us": sum(leaf_durs) / len(leaf_durs) * 1e3, "launches_timed": len(durs),
-                    "algorithmic_bytes_per_launch": bytes_per_launch,
-                    "levels_per_sim": dl / max(ds, 1), "note": "a launch moves ~2 MB for 1024 trees: it is bound by the "
-                    "dependent chain of one warp per tree (L2 / DRAM latency), not by bandwidth; see DESIGN.md section 3"}
         # bytes_reroot = 4 nfi + 2 K R + (nfi - K) R per tree, R = 8F + 13 + E (+4 weighted)
         R_row = 8 * F + 13 + E + (4 if weighted else 0)
         rr_bytes = (4 * int(rr_st[2]) + R_row * (int(rr_st[3]) + int(rr_st[2]))) / moves_r
@@ -432,11 +523,13 @@ def run_native(args, out):
                               "achieved": rr_achieved, "peak": peak, "unit": "GB/s", "frac": rr_achieved / peak,
                               "avg_launch_us": rr_avg_ms * 1e3, "algorithmic_bytes_per_launch": rr_bytes,
                               "rows_before": int(rr_st[2]) / moves_r / B, "rows_kept": int(rr_st[3]) / moves_r / B}
+    slib.tz_synth_set_programmatic(1 if use_pdl else 0)
+    del sp, one_move, load_inputs
 
     # ---------------- leg 3: e2e through the public Python API with host buffers -----------------------------------
     e2e = None
-    if not args.skip_e2e:
-        ev2 = new_eval()
+    if "e2e" in legs:
+        ev2 = new_eval(use_pdl)
         env = SyntheticEnv(game, B, env_offset=rank * B, device=dev)
         tree2 = ev2.init_batched(B, game.template_embedding(), device=dev)
         # the step's three random inputs live in ONE device buffer (views below), so the step costs one H2D copy
@@ -496,19 +589,100 @@ def run_native(args, out):
         t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B * S * K / float(t_e.item()), "unit": UNIT,
+        e2e = {"value": total_envs * S * K / float(t_e.item()), "unit": UNIT,
                "h2d_bytes_per_step": int(2 * B * F * 4 + B * 4), "d2h_bytes_per_step": int(B * 4 + B * F * 4),
                "ms_per_step": float(t_e.item()) / K * 1e3,
                "api": "step_env_and_evaluator(MCTS.evaluate + MCTS.step) captured in a CUDA graph by the caller; "
                       "host wall clock incl. pinned H2D of the step's noise inputs and D2H of actions + policy weights",
                "launches_per_step": int(api_launches)}
+        del tree2, ev2, env
+
+    res = {
+        "value": value, "ms_per_step": ms_per_step,
+        "per_step_ms": {"min": main["ms_min"], "median": main["ms_median"], "max": main["ms_max"]},
+        "levels_per_sim": main["levels_per_sim"], "launches_per_move": main["launches_per_move"], "clocks": main["clocks"],
+        "config": {"workload": desc, "envs_per_gpu": B, "envs_total": total_envs, "simulations": S, "max_nodes": N,
+                   "branching_factor": F, "embedding_bytes": E, "weighted": weighted, "discount": discount,
+                   "programmatic_dependent_launch": use_pdl, "levels_per_sim": main["levels_per_sim"],
+                   "sim_warps": args.sim_warps,
+                   "step": "one self-play move of all envs: root eval, set_root, S x (select, leaf, expand+backprop), "
+                           "root action, env step, re-root" + (", replay-buffer update (tz_replay_collect, capacity "
+                                                                f"{REPLAY_CAPACITY})" if with_replay else "")
+                           + (f", one cross-rank replay sample of {TRAIN_BATCH} rows and the gradient-mean all-reduce of "
+                              f"{GRAD_FLOATS * 4 >> 20} MiB over NCCL" if with_nccl else "")},
+        "ordinary_launches": (None if other is None else
+                              {"value": total_envs * S * K / (other["ms_total"] * 1e-3), "ms_per_step": other["ms_total"] / K,
+                               "note": "same moves with TzSearchCfg.programmatic = 0, the API default (the stand-in leaf kernel "
+                                       "launched ordinarily too)"}),
+        "roofline": roofline, "e2e": e2e,
+    }
+    res["config"].update(main["extra"])
+    return res
+
+
+def run_native(args, out):
+    import torch
+    import torch.distributed as dist
+
+    import turbozero_b200 as tz
+    from turbozero_b200 import _abi
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (native arm) needs a CUDA device; there is no CPU fallback for the search kernels")
+    cx = Ctx()
+    cx.args, cx.tz, cx._abi = args, tz, _abi
+    cx.world = int(os.environ.get("WORLD_SIZE", "1"))
+    cx.rank = int(os.environ.get("RANK", "0"))
+    cx.local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(cx.local)
+    cx.dev = torch.device("cuda", cx.local)
+    if cx.world > 1:
+        dist.init_process_group("nccl", device_id=cx.dev)
+    cx.lib, cx.slib = _abi.lib(), _abi.synth_lib()
+    cx.flush_buf = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=cx.dev)
+    world, rank = cx.world, cx.rank
+
+    wl = args.workload
+    name, B0, S, N, weighted, discount, desc = WORKLOADS[wl]
+    B = args.envs or B0
+    K, W = args.steps, max(args.warmup, 3)  # timing rule: never fewer than 3 warm-up steps
+
+    def pdl_for(w):
+        return args.pdl or (not args.no_pdl and w not in NO_PDL_BY_DEFAULT)
+
+    legs = {"ordinary"}
+    if not args.skip_roofline:
+        legs.add("roofline")
+    if not args.skip_e2e:
+        legs.add("e2e")
+    head = measure_workload(cx, wl, B, K, W, use_pdl=pdl_for(wl), legs=legs)
+
+    # ---------------- the configs BASELINE.json names for this GPU count --------------------------------------------
+    if args.named is not None:
+        named_wls = [w for w in args.named.split(",") if w]
+    else:
+        named_wls = (["cfg3"] if world in (2, 4, 8) else []) + (["cfg4", "cfg5"] if world == 8 else [])
+    named = []
+    for nw in named_wls:
+        nB = WORKLOADS[nw][1]
+        strong = None
+        if nw == "cfg3" and world > 1 and CFG3_TOTAL_ENVS % world == 0:
+            nB, strong = CFG3_TOTAL_ENVS // world, CFG3_TOTAL_ENVS  # configs[2] is ONE 4096-env job sharded over 2 / 4 / 8 GPUs
+        nK = max(3, min(K, 4 if nw == "cfg4" else 8))
+        r = measure_workload(cx, nw, nB, nK, 3, use_pdl=pdl_for(nw), legs=legs - {"ordinary"}, strong_total=strong)
+        entry = {"name": nw, "metric": METRIC, "unit": UNIT, "value": r["value"], "ms_per_step": r["ms_per_step"], "steps": nK,
+                 "warmup": 3, "per_step_ms": r["per_step_ms"], "scaling": "strong" if strong else "weak",
+                 "env_steps_per_sec": r["value"] / WORKLOADS[nw][2], "config": r["config"], "e2e": r["e2e"],
+                 "roofline": r["roofline"], "launches_per_step": r["launches_per_move"]}
+        named.append(entry)
 
     # ---------------- leg 4: CPU baseline (oracle port) on a bounded sample ---------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.skip_cpu:
+        seed = 1000 + rank
         CO, g, cgm, cfg, t, episode, core, payload = cpu_selfplay_setup(wl, B, 0, seed)
         threads = host_threads(CO)
-        dnc, rnc, uc = host_inputs(np.random.default_rng(2), 1, B, F)
+        dnc, rnc, uc = host_inputs(np.random.default_rng(2), 1, B, g.F)
         warm = 0.0
         while warm < 2.0:  # host cores of a shared box take a second or two to ramp up / schedule all threads
             warm += cpu_moves(CO, cgm, cfg, t, S, 1, dnc, rnc, uc, core, payload, episode, threads)
@@ -518,34 +692,30 @@ def run_native(args, out):
             moves_done += 1
         cpu = {"value": B * S * moves_done / spent, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": f"{moves_done} moves of {B} envs x {S} sims ({spent:.1f} s), tree-major C oracle, OpenMP over trees; "
-                         f"host has {os.cpu_count()} logical CPUs"}
+                         f"host has {os.cpu_count()} logical CPUs",
+               "numpy_port": numpy_oracle_baseline(wl, seed, seconds=min(6.0, args.cpu_seconds)),
+               "note": "the reference itself (JAX on the CPU backend) cannot run in this image; `value` is the multi-threaded C "
+                       "restatement (the strongest CPU number), `numpy_port` the literal per-tree NumPy restatement of the "
+                       "reference's array program (closest stand-in for its per-example dataflow, one thread)"}
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32+i32", "data": "synthetic",
-            "config": {"workload": desc, "envs_per_gpu": B, "envs_total": B * world, "simulations": S, "max_nodes": N,
-                       "branching_factor": F, "embedding_bytes": E, "weighted": weighted, "discount": discount,
-                       "l2": "not flushed" if args.no_flush else "flushed between steps (512 MiB fill, outside the per-step events)",
-                       "graph": not args.no_graph, "programmatic_dependent_launch": use_pdl,
-                       "ordinary_launches": (None if other_ms is None else
-                                             {"value": world * B * S * K / (other_ms * 1e-3), "ms_per_step": other_ms / K,
-                                              "note": "same moves with TzSearchCfg.programmatic = 0 (the stand-in leaf kernel "
-                                                      "launched ordinarily too)"}),
-                       "levels_per_sim": levels_per_sim,
-                       "step": "one self-play move of all envs: root eval, set_root, S x (select, leaf, expand+backprop), "
-                               "root action, env step, re-root" + (", replay-buffer update (tz_replay_collect, capacity "
-                                                                    f"{REPLAY_CAPACITY})" if with_replay else "")},
-            "clocks": clocks,
-            "env_steps_per_sec": value / S,  # the metric's second half: self-play env steps of the whole job per second
-            "gpu_launches": int(launches_per_move * K),
-            "launches_per_step": int(launches_per_move),
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": head["ms_per_step"], "per_step_ms": head["per_step_ms"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
+            "config": dict(head["config"],
+                           l2="not flushed" if args.no_flush else "flushed between steps (512 MiB fill, outside the per-step events)",
+                           graph=not args.no_graph, ordinary_launches=head["ordinary_launches"], named=named),
+            "ordinary_launches": head["ordinary_launches"],
+            "clocks": head["clocks"],
+            "env_steps_per_sec": head["value"] / S,  # the metric's second half: self-play env steps of the whole job per second
+            "gpu_launches": int(head["launches_per_move"] * K),
+            "launches_per_step": int(head["launches_per_move"]),
         }
-        if roofline:
-            line["roofline"] = roofline
-        if e2e:
-            line["e2e"] = e2e
+        if head["roofline"]:
+            line["roofline"] = head["roofline"]
+        if head["e2e"]:
+            line["e2e"] = head["e2e"]
         if cpu:
             line["cpu_baseline"] = cpu
         out.append(json.dumps(line))

@@ -95,6 +95,13 @@ uint64_t tz_synth_launch_count(void);
  * signals its own dependents -- the form TzSearchCfg.programmatic requires of a leaf kernel).  Returns the old setting. */
 int tz_synth_set_programmatic(int on);
 
+/* Measurement record of the leaf stand-in's launches, the twin of TzWork.timeline (include/tz_abi.h): while `rows_dev`
+ * (device uint64 [slots,4], slots a power of two, rows initialised to {~0, 0, 0, 0}) is set, launch number q of
+ * tz_synth_leaf (tz_synth_leaf_seq() = the next q) records %globaltimer ns {first warp in, last warp past its wait, last
+ * warp out, -} into row q mod slots.  NULL switches it off.  Launches captured into a CUDA graph keep their row. */
+int tz_synth_set_timeline(uint64_t* rows_dev, int slots);
+uint64_t tz_synth_leaf_seq(void);
+
 #ifdef __cplusplus
 }
 #endif

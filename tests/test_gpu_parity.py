@@ -233,3 +233,148 @@ def test_division_sequence_is_ieee_exact():
     for seed in (1, 2):
         _abi.check(_abi.lib().tz_selftest_div(1 << 29, seed, bad.data_ptr(), torch.cuda.current_stream().cuda_stream), "selftest")
     assert int(bad.item()) == 0
+
+
+# ---- round 2: the shapes bench.py times (BASELINE.json configs[2..4] per-GPU shares), against the oracle ----------------
+@pytest.mark.parametrize("envs", [1024, 2048])
+def test_othello_weighted_2_and_4_gpu_shares(envs):
+    """BASELINE.json configs[2] sharded over 4 / 2 GPUs: 1024 / 2048 envs per GPU x 200 simulations, N = 400, WeightedMCTS."""
+    s = Schedule(game=SN.make_game("othello", 3001), B=envs, N=400, S=200, moves=2, temperature=1.0, weighted=True)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), f"othello weighted, {envs} envs")
+
+
+def test_go_9x9_full_depth_256_envs():
+    """BASELINE.json configs[3] tree shape at full depth (N = 1600, 800 simulations, 82-way, 4 KB embedding rows) on a quarter
+    of the per-GPU batch, against the multi-threaded C oracle, through a replayed CUDA graph like the bench."""
+    s = Schedule(game=SN.make_game("go_9x9", 4002), B=256, N=1600, S=800, moves=2, temperature=1.0)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), "go_9x9 full depth, 256 envs")
+
+
+def test_2048_step_with_replay_update_at_bench_shape():
+    """The configs[4] step exactly as bench.py runs it on one GPU's share: 2048 envs x 100 simulations (N = 200, discount +1)
+    FOLLOWED IN THE SAME STEP by the replay-buffer update (tz_replay_collect fed from the move's outputs), three moves in a
+    replayed CUDA graph.  Trees / actions / policy weights against the C oracle; the buffer against oracle/replay_numpy.py
+    fed with the same per-move records."""
+    import torch
+    import turbozero_b200 as tz
+    from helpers import make_cuda_evaluator
+    from oracle import replay_numpy as RN
+    from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay
+
+    B, F, cap, moves = 2048, 4, 16, 3
+    s = Schedule(game=SN.make_game("2048", 5001), B=B, N=200, S=100, moves=moves, temperature=1.0, discount=1.0, programmatic=True)
+    ref = run_c_treemajor(s)
+    g = s.game
+    game = SyntheticGame(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
+    ev = make_cuda_evaluator(s, game)
+    sp = SyntheticSelfPlay(game, ev, B, dirichlet=True)
+    rb = tz.EpisodeReplayBuffer(capacity=cap)
+    obs0 = sp.state["core"].to(torch.float32)
+    rstate = rb.init(B, tz.BaseExperience(reward=torch.zeros((1,)), policy_weights=torch.zeros((F,)),
+                                          policy_mask=torch.zeros((F,), dtype=torch.bool), observation_nn=obs0[0].cpu(),
+                                          cur_player_id=torch.zeros((), dtype=torch.int32)))
+    x_obs, x_mask = torch.empty_like(obs0), torch.ones((B, F), dtype=torch.bool, device="cuda")
+    x_rew0, x_rew = torch.zeros((B, 1), device="cuda"), torch.empty((B, 1), device="cuda")
+    x_player = torch.zeros((B,), dtype=torch.int32, device="cuda")
+    x_trunc = torch.zeros((B,), dtype=torch.uint8, device="cuda")
+
+    def one_move():
+        x_obs.copy_(sp.state["core"])
+        sp.move()
+        x_rew.copy_(sp.reset_flag.unsqueeze(1))
+        exp = tz.BaseExperience(reward=x_rew0, policy_weights=sp.policy_weights, policy_mask=x_mask, observation_nn=x_obs,
+                                cur_player_id=x_player)
+        rb.collect_update(rstate, [exp], x_rew, sp.reset_flag, x_trunc)
+
+    tmpl_np = {"reward": np.zeros((1,), np.float32), "policy_weights": np.zeros((F,), np.float32), "policy_mask": np.zeros((F,), bool),
+               "observation_nn": np.zeros((4,), np.float32), "cur_player_id": np.zeros((), np.int32)}
+    rs = RN.init(B, cap, tmpl_np)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    cg = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(cg, stream=side):
+            one_move()
+    torch.cuda.current_stream().wait_stream(side)
+    actions = np.zeros((moves, B), np.int32)
+    pw = np.zeros((moves, B, F), np.float32)
+    for m in range(moves):
+        sp.dir_noise.copy_(torch.from_numpy(s.dir_noise[m]))
+        sp.root_noise.copy_(torch.from_numpy(s.root_noise[m]))
+        sp.uniform01.copy_(torch.from_numpy(s.uniform01[m]))
+        obs_before = sp.state["core"].to(torch.float32).cpu().numpy()
+        cg.replay()
+        torch.cuda.synchronize()
+        actions[m], pw[m] = sp.action.cpu().numpy(), sp.policy_weights.cpu().numpy()
+        done = sp.reset_flag.cpu().numpy().astype(bool)
+        e = {"reward": np.zeros((B, 1), np.float32), "policy_weights": pw[m], "policy_mask": np.ones((B, F), bool),
+             "observation_nn": obs_before, "cur_player_id": np.zeros((B,), np.int32)}
+        RN.collect_update(rs, [e], done.astype(np.float32).reshape(B, 1), done, np.zeros((B,), bool), cap)
+    assert np.array_equal(ref.actions, actions) and np.array_equal(ref.pw, pw)
+    from helpers import tree_to_numpy
+    assert_trees_equal(ref.arrays, tree_to_numpy(sp.tree), "2048 step with replay update")
+    assert np.array_equal(rstate.populated.cpu().numpy(), rs.populated) and np.array_equal(rstate.has_reward.cpu().numpy(), rs.has_reward)
+    assert np.array_equal(rstate.next_idx.cpu().numpy(), rs.next_idx)
+    for k in tmpl_np:
+        assert np.array_equal(getattr(rstate.buffer, k).cpu().numpy(), rs.buffer[k]), k
+
+
+def test_masked_reset_touches_only_the_flagged_trees():
+    """MCTS.reset(state, mask): Tree.reset (tree.py:272-278) for the flagged trees, the others bit-for-bit untouched."""
+    import torch
+    from helpers import make_cuda_evaluator, tree_to_numpy
+    from turbozero_b200.synthetic import SyntheticGame
+
+    s = Schedule(**CASES["c4"])
+    g = s.game
+    game = SyntheticGame(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
+    ev = make_cuda_evaluator(s, game)
+    tree = ev.init_batched(s.B, game.template_embedding())
+    state, _ = game.init_states(s.B)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    ev.evaluate(None, tree, state, None, None, None, leaf_fn=game.leaf_fn, root_noise=dev(s.root_noise[0]), uniform01=dev(s.uniform01[0]),
+                dirichlet_noise=dev(s.dir_noise[0]))
+    before = tree_to_numpy(tree)
+    mask = torch.tensor([b % 3 == 1 for b in range(s.B)], device="cuda")
+    ev.reset(tree, mask=mask)
+    after = tree_to_numpy(tree)
+    fresh = tree_to_numpy(ev.init_batched(s.B, game.template_embedding()))
+    m = mask.cpu().numpy()
+    assert m.any() and not m.all() and (before["next_free_idx"] > 1).all()
+    for k in before:
+        assert np.array_equal(after[k][m], fresh[k][m]), f"{k}: flagged trees must be empty"
+        assert np.array_equal(after[k][~m], before[k][~m]), f"{k}: unflagged trees must be untouched"
+    ev.reset(tree)  # and the unmasked form resets everything
+    assert_trees_equal(fresh, tree_to_numpy(tree), "full reset")
+
+
+def test_launch_timeline_records_every_search_and_leaf_launch():
+    """TzWork.timeline / tz_synth_set_timeline (what bench.py's roofline leg reads): every launch of a replayed move writes
+    its row, rows are ordered in time, and the trees are the oracle's with the record on."""
+    import torch
+    from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay
+    from helpers import make_cuda_evaluator, tree_to_numpy
+
+    for programmatic in (False, True):
+        s = Schedule(**CASES["c4"], programmatic=programmatic)
+        g = s.game
+        game = SyntheticGame(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
+        ev = make_cuda_evaluator(s, game)
+        sp = SyntheticSelfPlay(game, ev, s.B, dirichlet=True)
+        sp.timeline_begin()
+        for m in range(s.moves):
+            sp.dir_noise.copy_(torch.from_numpy(s.dir_noise[m]))
+            sp.root_noise.copy_(torch.from_numpy(s.root_noise[m]))
+            sp.uniform01.copy_(torch.from_numpy(s.uniform01[m]))
+            sp.timeline_clear()
+            mark = sp.timeline_mark()
+            sp.move()
+            torch.cuda.synchronize()
+            ts, tl = sp.timeline_read(mark, s.S + 1, s.S)
+            assert (ts[:, 0] > 0).all() and (ts[:, 2] >= ts[:, 0]).all(), "every search launch wrote first-in / last-out"
+            assert (tl[:, 0] > 0).all() and (tl[:, 2] >= tl[:, 1]).all() and (tl[:, 1] >= tl[:, 0]).all()
+            assert (ts[1:, 2] > ts[:-1, 2]).all() and (tl[1:, 2] > tl[:-1, 2]).all(), "launches complete in stream order"
+            assert (tl[:, 2] > ts[:-1, 0]).all() and (ts[1:, 2] > tl[:, 2]).all(), "leaf s sits between search launches s and s+1"
+        sp.timeline_end()
+        ref = run_c_treemajor(s)
+        assert_trees_equal(ref.arrays, tree_to_numpy(sp.tree), f"timeline on, programmatic={programmatic}")

@@ -117,6 +117,8 @@ TZ_SYNTH_SYMBOLS = {
     "tz_synth_leaf_cb_timed": (C.c_int, [_vp, C.c_int, _P(TzWork), _vp]),
     "tz_synth_timed_collect": (C.c_int, [_vp, _vp]),
     "tz_synth_set_programmatic": (C.c_int, [C.c_int]),
+    "tz_synth_set_timeline": (C.c_int, [_vp, C.c_int]),
+    "tz_synth_leaf_seq": (C.c_uint64, []),
 }
 
 

@@ -20,6 +20,11 @@ constexpr int MAX_NC = 16;
 
 std::atomic<uint64_t> g_launches{0};
 std::atomic<int> g_programmatic{0};  // tz_synth_set_programmatic
+// optional per-launch record of k_leaf in the product build (tz_synth_set_timeline), the twin of TzWork.timeline
+std::atomic<unsigned long long*> g_tl_rows{nullptr};
+std::atomic<uint32_t> g_tl_slots{0};
+std::atomic<uint64_t> g_leaf_seq{0};
+__device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 #ifdef TZ_PROFILE  // diagnostic build (libtz_synth_prof.so): per-launch timeline of k_leaf, see scripts/timeline.py
 __device__ unsigned long long g_tl[4 * 1024];  // {first warp in, last warp past griddepcontrol.wait, last warp out, -}
@@ -121,12 +126,13 @@ __global__ void __launch_bounds__(THREADS) k_root(const TzSynthGame g, const int
 __global__ void __launch_bounds__(THREADS) k_leaf(const TzSynthGame g, const int B, const int32_t* __restrict__ parent_core,
                                                 const int32_t* __restrict__ action, float* __restrict__ policy,
                                                 float* __restrict__ value, uint8_t* __restrict__ terminated, int32_t* new_core,
-                                                uint8_t* new_payload, const int pdl_and_slot) {
+                                                uint8_t* new_payload, const int pdl_and_slot, unsigned long long* tl_row) {
   const int pdl = pdl_and_slot & 1;
   [[maybe_unused]] const int tl_slot = pdl_and_slot >> 1;  // diagnostic build: timeline slot of this launch
   const int b = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   TZ_TL(atomicMin, tl_slot, 0);
+  if (tl_row && lane == 0) atomicMin(tl_row + 0, gtime_ns());
   const int F = g.F, nc = (F + 31) >> 5;
   const int32_t* pc = parent_core + 4 * (size_t)b;
   // Programmatic dependent launch, the form TzSearchCfg.programmatic asks of a leaf kernel: wait for the preceding
@@ -140,6 +146,7 @@ __global__ void __launch_bounds__(THREADS) k_leaf(const TzSynthGame g, const int
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
   TZ_TL(atomicMax, tl_slot, 1);
+  if (tl_row && lane == 0) atomicMax(tl_row + 1, gtime_ns());
   const uint32_t h2 = tz_synth_step_h((uint32_t)pc[0], (uint32_t)action[b]);
   const int d2 = pc[1] + 1;
   const int term = tz_synth_terminal(h2, d2, g.tau1024, g.max_depth);
@@ -159,6 +166,7 @@ __global__ void __launch_bounds__(THREADS) k_leaf(const TzSynthGame g, const int
   }
   write_state(g, h2, d2, 1 - pc[2], new_core + 4 * (size_t)b, new_payload ? new_payload + (size_t)b * g.payload_bytes : nullptr, lane);
   TZ_TL(atomicMax, tl_slot, 2);
+  if (tl_row && lane == 0) atomicMax(tl_row + 2, gtime_ns());
 }
 
 __global__ void __launch_bounds__(THREADS) k_env_step(const TzSynthGame g, const int B, const int env_offset,
@@ -218,6 +226,15 @@ int tz_synth_debug_timeline(unsigned long long* out, int reset) {  // diagnostic
 }
 #endif
 
+int tz_synth_set_timeline(uint64_t* rows_dev, int slots) {
+  if (rows_dev && (slots <= 0 || (slots & (slots - 1)) != 0)) return TZ_EINVAL;
+  g_tl_slots.store(rows_dev ? (uint32_t)slots : 0u, std::memory_order_relaxed);
+  g_tl_rows.store(reinterpret_cast<unsigned long long*>(rows_dev), std::memory_order_relaxed);
+  return TZ_OK;
+}
+
+uint64_t tz_synth_leaf_seq(void) { return g_leaf_seq.load(std::memory_order_relaxed); }
+
 int tz_synth_set_programmatic(int on) { return g_programmatic.exchange(on ? 1 : 0, std::memory_order_relaxed); }
 
 int tz_synth_init_states(const TzSynthGame* g, int B, int env_offset, const int32_t* episode, int32_t* core,
@@ -250,6 +267,8 @@ int tz_synth_leaf(const TzSynthGame* g, int B, const int32_t* parent_core, const
 #else
   const int tl_slot = 0;
 #endif
+  unsigned long long* tl_row = g_tl_rows.load(std::memory_order_relaxed);
+  if (tl_row) tl_row += 4 * (g_leaf_seq.fetch_add(1, std::memory_order_relaxed) & (uint64_t)(g_tl_slots.load(std::memory_order_relaxed) - 1));
   if (g_programmatic.load(std::memory_order_relaxed)) {
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid_for(B));
@@ -260,12 +279,12 @@ int tz_synth_leaf(const TzSynthGame* g, int B, const int32_t* parent_core, const
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, k_leaf, *g, B, parent_core, action, policy, value, terminated, new_core, new_payload, 1 | tl_slot);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, k_leaf, *g, B, parent_core, action, policy, value, terminated, new_core, new_payload, 1 | tl_slot, tl_row);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e == cudaSuccess ? TZ_OK : (int)e;
   }
   k_leaf<<<grid_for(B), THREADS, 0, (cudaStream_t)stream>>>(*g, B, parent_core, action, policy, value, terminated, new_core,
-                                                          new_payload, 0 | tl_slot);
+                                                          new_payload, 0 | tl_slot, tl_row);
   return status();
 }
 

@@ -216,6 +216,41 @@ class SyntheticSelfPlay:
     def pipelines(self) -> int:
         return len(self.lanes)
 
+    # --- measurement: in-step launch timeline (TzWork.timeline + tz_synth_set_timeline), single lane only ---
+    TL_SLOTS = 2048
+
+    def timeline_begin(self) -> None:
+        """From now on every per-simulation search launch and every leaf launch issued (or captured) by this object
+        records {first warp in, last warp has its inputs, last warp out} in %globaltimer ns."""
+        assert len(self.lanes) == 1
+        init = torch.zeros((self.TL_SLOTS, 4), dtype=torch.int64, device=self.dev)
+        init[:, 0] = -1  # ~0 as uint64
+        self._tl_init = init
+        self._tl_search, self._tl_leaf = init.clone(), init.clone()
+        self.lanes[0].work.timeline = self._tl_search.data_ptr()
+        self.lanes[0].work.timeline_slots = self.TL_SLOTS
+        _abi.check(_abi.synth_lib().tz_synth_set_timeline(self._tl_leaf.data_ptr(), self.TL_SLOTS), "tz_synth_set_timeline")
+
+    def timeline_mark(self):
+        """(search seq, leaf seq) of the next launches: call right before issuing / capturing the move to be read."""
+        return int(_abi.lib().tz_launch_seq()), int(_abi.synth_lib().tz_synth_leaf_seq())
+
+    def timeline_clear(self) -> None:
+        self._tl_search.copy_(self._tl_init)
+        self._tl_leaf.copy_(self._tl_init)
+
+    def timeline_read(self, mark, n_search: int, n_leaf: int):
+        """Rows of the `n_search` search launches / `n_leaf` leaf launches issued after `mark`, as int64 numpy [n,3]."""
+        s0, l0 = mark
+        idx_s = (torch.arange(n_search, device=self.dev) + s0) % self.TL_SLOTS
+        idx_l = (torch.arange(n_leaf, device=self.dev) + l0) % self.TL_SLOTS
+        return self._tl_search[idx_s, :3].cpu().numpy(), self._tl_leaf[idx_l, :3].cpu().numpy()
+
+    def timeline_end(self) -> None:
+        self.lanes[0].work.timeline = None
+        self.lanes[0].work.timeline_slots = 0
+        _abi.check(_abi.synth_lib().tz_synth_set_timeline(None, 0), "tz_synth_set_timeline")
+
     def launches_per_move(self) -> int:
         S = self.ev.num_iterations
         # root, set_root, select + S leaf + S expand, root_action, env_step, reroot -- per lane
