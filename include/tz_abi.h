@@ -142,7 +142,10 @@ typedef struct TzWork {
                                no longer fit the 32-level ring of `path` (level l of a path of length L > 32 is kept here
                                for l < L - 32).  With it a deep backup processes 32 levels per memory round trip like the
                                ring does; without it (NULL) levels above the ring are reached by chasing parents[], one
-                               dependent round trip each.  path_spill_cap >= max_nodes - 32 covers every possible path. */
+                               dependent round trip each.  path_spill_cap >= max_nodes - 32 covers every possible path.
+                               With TzSearchCfg.sim_warps > 1 (a CTA per tree) the WHOLE path is kept here linearly (level l
+                               at entry l) and `path` only carries {tag, length, end child}: that form needs
+                               path_spill_cap >= max_nodes (otherwise the library uses one warp per tree). */
   int32_t path_spill_cap;   /* entries per tree in path_spill */
   int32_t timeline_slots;   /* rows of `timeline` (a power of two), 0 = none */
   uint64_t* timeline;       /* optional [timeline_slots,4] measurement record of the per-simulation launches that use this

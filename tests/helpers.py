@@ -43,6 +43,7 @@ class Schedule:
     c: float = 1.0
     fma_backup: bool = False
     programmatic: bool = False  # TzSearchCfg.programmatic (CUDA path only: launch mechanics, not semantics)
+    sim_warps: int = 0  # TzSearchCfg.sim_warps (CUDA path only: warps per tree, not semantics)
     tiebreak_noise: float = 1e-8
     seed: int = 0
     env_offset: int = 0
@@ -276,7 +277,9 @@ def make_cuda_evaluator(s: Schedule, game):
               tiebreak_noise=s.tiebreak_noise, persist_tree=s.persist_tree)
     if s.weighted:
         kw["q_temperature"] = s.q_temperature
-    return make_synthetic_evaluator(base, game, dir_eps=s.dir_eps, fma_backup=s.fma_backup, programmatic=s.programmatic, **kw)
+    ev = make_synthetic_evaluator(base, game, dir_eps=s.dir_eps, fma_backup=s.fma_backup, programmatic=s.programmatic, **kw)
+    ev.sim_warps = s.sim_warps
+    return ev
 
 
 def run_cuda_api(s: Schedule, fused: bool = True, snapshots: bool = False) -> Result:

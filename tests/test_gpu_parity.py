@@ -378,3 +378,104 @@ def test_launch_timeline_records_every_search_and_leaf_launch():
         sp.timeline_end()
         ref = run_c_treemajor(s)
         assert_trees_equal(ref.arrays, tree_to_numpy(sp.tree), f"timeline on, programmatic={programmatic}")
+
+
+# ---- a CTA of W warps per tree (TzSearchCfg.sim_warps, k_sim_wide): same trees, bit for bit ---------------------------
+WIDE_CASES = ["c4", "othello_weighted", "othello_weighted_T05", "go_muzero", "deep_discount09", "wide_F300", "very_deep", "no_persist",
+              "g2048_pos_discount", "fma"]
+
+
+@pytest.mark.parametrize("name", WIDE_CASES)
+@pytest.mark.parametrize("warps", [2, 4, 8])
+def test_cta_per_tree_c_loop_vs_oracle(name, warps):
+    s = Schedule(**CASES[name], sim_warps=warps)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=(warps == 4)), f"{name}, {warps} warps per tree")
+
+
+@pytest.mark.parametrize("name", ["c4", "othello_weighted", "weighted_qT0", "go_muzero", "ttt_T0"])
+@pytest.mark.parametrize("warps", [2, 4])
+def test_cta_per_tree_python_api_vs_oracle(name, warps):
+    """Through MCTS.evaluate (one launch per simulation from Python), with the per-move self-tests of run_cuda_api."""
+    s = Schedule(**CASES[name], sim_warps=warps)
+    ref = run_c_stepwise(s, snapshots=True)
+    got = run_cuda_api(s, fused=True, snapshots=True)
+    for m, (x, y) in enumerate(zip(ref.snapshots, got.snapshots)):
+        assert_trees_equal(x, y, f"{name}: after search of move {m}")
+    _compare(ref, got, name)
+    assert np.array_equal(ref.stats, got.stats)
+
+
+@pytest.mark.parametrize("name", ["c4", "othello_weighted", "very_deep"])
+def test_cta_per_tree_unfused_and_programmatic(name):
+    s = Schedule(**CASES[name], sim_warps=4)
+    _compare(run_c_stepwise(s), run_cuda_api(s, fused=False), name + " unfused")
+    s = Schedule(**CASES[name], sim_warps=4, programmatic=True)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), name + " programmatic")
+
+
+@pytest.mark.parametrize("name", list(DEEP))
+@pytest.mark.parametrize("warps", [2, 4, 8])
+def test_cta_per_tree_deep_paths_vs_oracle(name, warps):
+    """Paths of 60-150 levels: several 32 W-level passes (W = 2), the vote over a path longer than one pass."""
+    s = Schedule(**DEEP[name], sim_warps=warps)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s), f"{name}, {warps} warps")
+
+
+def test_cta_per_tree_deep_weighted():
+    s = Schedule(game=G(F=40, payload_bytes=8, rho256=2, tau1024=0, max_depth=600, seed=33), B=4, N=160, S=140, moves=3,
+                 temperature=1.0, weighted=True, sim_warps=2)
+    ref = run_c_treemajor(s)
+    assert ref.stats[:, 0].sum() / max(ref.stats[:, 1].sum(), 1) > 15, "the schedule is meant to produce deep paths"
+    _compare(ref, run_cuda_selfplay(s), "deep weighted, 2 warps")
+    s4 = Schedule(game=s.game, B=4, N=160, S=140, moves=3, temperature=1.0, weighted=True, sim_warps=4)
+    _compare(ref, run_cuda_selfplay(s4, graph=True), "deep weighted, 4 warps")
+
+
+def test_cta_per_tree_rebuilds_a_foreign_path_record():
+    """select by the one-warp kernel, expand by the CTA-per-tree kernel (and the other way round): the path record of the
+    other form is not trusted; the kernel rebuilds the path from parents[] / edge_map -- same trees as the oracle."""
+    import torch
+    from helpers import make_cuda_evaluator, tree_to_numpy
+    from turbozero_b200.synthetic import SyntheticGame
+
+    for name in ("c4", "go_muzero", "othello_weighted"):
+        s = Schedule(**CASES[name])
+        ref = run_c_stepwise(s)
+        g = s.game
+        game = SyntheticGame(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
+        ev = make_cuda_evaluator(s, game)
+        tree = ev.init_batched(s.B, game.template_embedding())
+        state, episode = game.init_states(s.B, s.env_offset)
+        reset_flag = torch.zeros((s.B,), dtype=torch.uint8, device="cuda")
+        dev = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        actions = np.zeros((s.moves, s.B), np.int32)
+        for m in range(s.moves):
+            ev.update_root(None, tree, state, None, dirichlet_noise=dev(s.dir_noise[m]))
+            for it in range(s.S):
+                ev.sim_warps = 1 if (it + m) % 2 == 0 else 4  # traverse with one form ...
+                ev.traverse(tree)
+                ev.sim_warps = 4 if (it + m) % 2 == 0 else 1  # ... expand + backprop with the other
+                sc = tree._scratch
+                w, keep = ev._leaf_work(None, tree, sc, None, None, game.leaf_fn, None)
+                import ctypes as C
+                from turbozero_b200 import _abi
+                cfg = ev._cfg()
+                _abi.check(_abi.lib().tz_expand_backprop(C.byref(tree.struct()), C.byref(cfg), C.byref(w),
+                                                         torch.cuda.current_stream().cuda_stream), "tz_expand_backprop")
+            act, _ = ev.sample_root_action(None, tree, root_noise=dev(s.root_noise[m]), uniform01=dev(s.uniform01[m]))
+            actions[m] = act.cpu().numpy()
+            game.env_step(state, act, episode, reset_flag, s.env_offset)
+            ev.step(tree, act, reset_mask=reset_flag)
+        assert np.array_equal(ref.actions, actions), name
+        assert_trees_equal(ref.arrays, tree_to_numpy(tree), name + ": mixed path-record forms")
+
+
+def test_cta_per_tree_at_bench_shapes():
+    """configs[2] (othello weighted, 512 envs) and configs[3] (go_9x9, 128 envs at full depth) with the library's default
+    (4 warps per tree for F > 32) and with 8 / 2 warps."""
+    for warps in (0, 8):
+        s = Schedule(game=SN.make_game("go_9x9", 4003), B=128, N=1600, S=800, moves=2, temperature=1.0, sim_warps=warps)
+        _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), f"go_9x9, sim_warps={warps}")
+    for warps in (0, 2):
+        s = Schedule(game=SN.make_game("othello", 3002), B=512, N=400, S=200, moves=2, temperature=1.0, weighted=True, sim_warps=warps)
+        _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), f"othello weighted, sim_warps={warps}")

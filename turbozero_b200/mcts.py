@@ -53,8 +53,9 @@ class _Scratch:
         self.parent = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.action = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.path = torch.zeros((B, _abi.TZ_PATH_STRIDE), dtype=torch.int32, device=dev)
-        # levels of paths deeper than the 32-level ring (TzWork.path_spill): every possible path fits
-        self.path_spill = torch.zeros((B, max(tree.capacity - _abi.TZ_PATH_CAP, 1), 2), dtype=torch.int32, device=dev)
+        # TzWork.path_spill: the levels of paths deeper than the 32-level ring (one warp per tree), or the whole path
+        # record (a CTA per tree, TzSearchCfg.sim_warps > 1): max_nodes entries hold every possible path in both forms
+        self.path_spill = torch.zeros((B, max(tree.capacity, 1), 2), dtype=torch.int32, device=dev)
         self.emb_parent = [torch.zeros((B, *shape), dtype=dt, device=dev) for shape, dt in tree.emb_leaf_shapes()]
         self.emb_parent_tree = tree.unflatten_embedding(self.emb_parent)
         self.select_only = self.work()

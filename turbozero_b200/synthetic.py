@@ -190,7 +190,7 @@ class SyntheticSelfPlay:
         self.w_action = torch.zeros((B,), dtype=torch.int32, device=dev)
         self.w_path = torch.zeros((B, _abi.TZ_PATH_STRIDE), dtype=torch.int32, device=dev) if use_path else None
         N_ = evaluator.max_nodes
-        self.w_path_spill = (torch.zeros((B, max(N_ - _abi.TZ_PATH_CAP, 1), 2), dtype=torch.int32, device=dev)
+        self.w_path_spill = (torch.zeros((B, max(N_, 1), 2), dtype=torch.int32, device=dev)
                              if (use_path and use_spill) else None)
         self.w_policy = torch.empty((B, F), dtype=f32, device=dev)
         self.w_value = torch.empty((B,), dtype=f32, device=dev)
