@@ -81,13 +81,17 @@ def reroot(name, B, S, N, warps, weighted):
         sp.move()
         torch.cuda.synchronize()
         lib.tz_debug_prof_gt(gbuf, nw)
-        rows = [[gbuf[16 * i + k] for k in range(11)] for i in range(nw)]
+        rows = [[gbuf[16 * i + k] for k in range(15)] for i in range(nw)]
         live = [r for r in rows if r[10] > 0 and all(r[k] > 0 for k in range(9))]  # re-rooted trees with at least one chunk
         if live:
             nfi = statistics.mean(r[9] for r in live)
             cnt = statistics.mean(r[10] for r in live)
             report(f"k_reroot_bulk {name} B={B}: move {rep}, {len(live)} re-rooted trees, rows before {nfi:.0f} kept {cnt:.0f}, ns", names,
                    [r[:9] for r in live])
+            ch = [r[14] for r in live]
+            print(f"  chunks per tree: mean {statistics.mean(ch):.1f} max {max(ch)}; per chunk (thread 0, mean over trees): issue "
+                  f"{statistics.mean(r[11] / max(r[14], 1) for r in live):.0f} ns, wait {statistics.mean(r[12] / max(r[14], 1) for r in live):.0f} ns, "
+                  f"scatter {statistics.mean(r[13] / max(r[14], 1) for r in live):.0f} ns")
 
 
 if __name__ == "__main__":

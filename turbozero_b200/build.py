@@ -24,11 +24,14 @@ NVCC_FLAGS = [
     "-lineinfo",
     "-fmad=false",  # every float op individually rounded: reference op order, bit-exact vs the oracle
     "-Xcompiler", "-fPIC",
-    "-shared",
 ]
 
+# one translation unit per kernel family / register-chunk count: they compile in parallel (the per-simulation kernels are
+# templates with ~100 instantiations; one TU took 3 minutes)
 TARGETS = {
-    "libtz_b200.so": ["csrc/tz_kernels.cu", "csrc/tz_replay.cu"],
+    "libtz_b200.so": ["csrc/tz_kernels.cu", "csrc/tz_replay.cu", "csrc/tz_reroot.cu", "csrc/tz_sim_nc1.cu", "csrc/tz_sim_nc2.cu",
+                      "csrc/tz_sim_nc3.cu", "csrc/tz_sim_nc4.cu", "csrc/tz_sim_nc8.cu", "csrc/tz_sim_nc16.cu",
+                      "csrc/tz_wide_plain.cu", "csrc/tz_wide_weighted.cu"],
     "libtz_synth.so": ["csrc/tz_synth.cu"],
 }
 
@@ -48,25 +51,47 @@ def _digest(paths) -> str:
     return h.hexdigest()
 
 
-def build(force: bool = False, verbose: bool = False) -> None:
+def _compile(cmd):
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    return cmd, res
+
+
+def build(force: bool = False, verbose: bool = False, extra_flags=(), suffix: str = "") -> None:
+    """Compiles every translation unit of every target to an object file (in parallel) and links the shared libraries.
+    `extra_flags` / `suffix` serve the diagnostic build (scripts/build_prof.sh: -DTZ_PROFILE -rdc=true -> lib*_prof.so)."""
+    from concurrent.futures import ThreadPoolExecutor
+
     LIB_DIR.mkdir(exist_ok=True)
-    headers = sorted(INCLUDE.glob("*.h"))
+    obj_dir = LIB_DIR / ("obj" + suffix)
+    headers = sorted(INCLUDE.glob("*.h")) + sorted((PKG / "csrc").glob("*.cuh"))
     for out_name, srcs in TARGETS.items():
-        out = LIB_DIR / out_name
+        out = LIB_DIR / out_name.replace(".so", suffix + ".so")
         src_paths = [PKG / s for s in srcs]
-        stamp = LIB_DIR / (out_name + ".sha256")
-        want = _digest(src_paths + headers)
+        stamp = LIB_DIR / (out.name + ".sha256")
+        want = _digest(src_paths + headers) + " " + " ".join(extra_flags)
         if not force and out.exists() and stamp.exists() and stamp.read_text().strip() == want:
             continue
-        cmd = [_nvcc(), *NVCC_FLAGS, f"-I{INCLUDE}", *map(str, src_paths), "-o", str(out)]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-            print(" ".join(cmd), file=sys.stderr)
-        res = subprocess.run(cmd, capture_output=True, text=True)
+        obj_dir.mkdir(exist_ok=True)
+        jobs = []
+        for sp in src_paths:
+            obj = obj_dir / (sp.stem + ".o")
+            cmd = [_nvcc(), *NVCC_FLAGS, *extra_flags, f"-I{INCLUDE}", "-c", str(sp), "-o", str(obj)]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+            jobs.append((cmd, obj))
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1)) as pool:
+            results = list(pool.map(_compile, [j[0] for j in jobs]))
+        for cmd, res in results:
+            if res.returncode != 0:
+                raise RuntimeError(f"nvcc failed for {out_name}:\n{' '.join(cmd)}\n{res.stdout}\n{res.stderr}")
+            if verbose:
+                print(" ".join(cmd), file=sys.stderr)
+                print(res.stderr, file=sys.stderr)
+        link = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", *[f for f in extra_flags if f.startswith("-rdc")],
+                "-Xcompiler", "-fPIC", "-shared", *[str(j[1]) for j in jobs], "-o", str(out)]
+        res = subprocess.run(link, capture_output=True, text=True)
         if res.returncode != 0:
-            raise RuntimeError(f"nvcc failed for {out_name}:\n{res.stdout}\n{res.stderr}")
-        if verbose:
-            print(res.stderr, file=sys.stderr)
+            raise RuntimeError(f"link failed for {out_name}:\n{' '.join(link)}\n{res.stdout}\n{res.stderr}")
         stamp.write_text(want + "\n")
 
 
@@ -91,4 +116,7 @@ def build_jax_ffi() -> Path:
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv, verbose="-v" in sys.argv)
+    if "--prof" in sys.argv:  # diagnostic build with in-kernel phase clocks: lib*_prof.so (scripts/phase_*.py, scripts/timeline.py)
+        build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=("-DTZ_PROFILE", "-rdc=true"), suffix="_prof")
+    else:
+        build(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -1,0 +1,6 @@
+// k_sim for trees with up to 96 actions (3 register chunks per lane): see tz_sim.cuh
+#include "tz_sim.cuh"
+
+namespace tz_internal {
+int launch_sim_nc3(const SimLaunch& L, cudaStream_t s) { return launch_sim_nc<3>(L, s); }
+}  // namespace tz_internal
