@@ -63,10 +63,25 @@ def wide(name, B, S, N, warps, weighted):
         if s < S // 2 or s % 8:
             continue
         lib.tz_debug_prof_gt(gbuf, nw)
-        acc.append([[gbuf[16 * i + k] for k in range(7)] for i in range(nw)])
+        acc.append([[gbuf[16 * i + k] for k in range(9)] for i in range(nw)])
     # median over sampled launches of per-launch summaries
     rows = acc[len(acc) // 2]
-    report(f"k_sim_wide {name} B={B} S={S} warps={warps} weighted={weighted}: one launch (of {len(acc)} sampled), ns", names, rows)
+    report(f"k_sim_wide {name} B={B} S={S} warps={warps} weighted={weighted}: one launch (of {len(acc)} sampled), ns", names,
+           [r[:7] for r in rows])
+    # per-level cost of the decisions phase: (stamp3 - stamp2) against the path length, all sampled launches pooled
+    import collections
+    byL = collections.defaultdict(list)
+    chain = collections.defaultdict(list)
+    for rr in acc:
+        for r in rr:
+            if r[8] > 0:
+                byL[min(int(r[8]), 64) // 4 * 4].append(r[3] - r[2])
+                if weighted and r[7] > r[2]:
+                    chain[min(int(r[8]), 64) // 4 * 4].append(r[7] - r[2])
+    print("  decisions phase by path length L (bucketed by 4): L, trees, median ns" + (", median chain ns" if weighted else ""))
+    for Lb in sorted(byL):
+        extra = f" {statistics.median(chain[Lb]):8.0f}" if (weighted and chain[Lb]) else ""
+        print(f"    {Lb:3d}+ {len(byL[Lb]):7d} {statistics.median(byL[Lb]):8.0f}{extra}")
     firsts = [max(r[6] for r in rr) - min(r[0] for r in rr) for rr in acc]
     print(f"  first-in -> last-out over the sampled launches: median {statistics.median(firsts)} ns, max {max(firsts)} ns")
 

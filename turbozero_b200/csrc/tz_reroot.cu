@@ -479,14 +479,15 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #else
 #define TZ_RSTAMP(i) do { } while (0)
 #endif
-__global__ void __launch_bounds__(REROOT2_THREADS) k_reroot_bulk(const __grid_constant__ RerootP P, const int32_t* __restrict__ action,
+template <int NTHR>
+__global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ RerootP P, const int32_t* __restrict__ action,
                                                                const uint8_t* __restrict__ reset_flag, const int persist_tree) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  __shared__ int wsum[REROOT2_THREADS / 32];
+  __shared__ int wsum[NTHR / 32];
   __shared__ __align__(8) uint64_t bar;
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
-  constexpr int nthr = REROOT2_THREADS;
+  constexpr int nthr = NTHR;
   const int N = P.N, F = P.F;
   uint8_t* const stage = smem_raw;
   int32_t* const trans = reinterpret_cast<int32_t*>(smem_raw + P.stage_bytes);  // old index -> new index (or -1)
@@ -541,7 +542,7 @@ __global__ void __launch_bounds__(REROOT2_THREADS) k_reroot_bulk(const __grid_co
       __syncthreads();
       int off = 0, total = 0;
 #pragma unroll
-      for (int k = 0; k < REROOT2_THREADS / 32; ++k) {
+      for (int k = 0; k < NTHR / 32; ++k) {
         const int sct = wsum[k];
         off += k < warp ? sct : 0;
         total += sct;
@@ -592,6 +593,11 @@ __global__ void __launch_bounds__(REROOT2_THREADS) k_reroot_bulk(const __grid_co
             for (int r = tid; r < rows; r += nthr) cp_async4(st + 4 * (size_t)r, src + 4 * (size_t)src_of[s0 + r]);
           } else if (unit == 16) {
             for (int r = tid; r < rows; r += nthr) cp_async16(st + 16 * (size_t)r, src + 16 * (size_t)src_of[s0 + r]);
+          } else if (unit == 5) {  // one-byte rows: the aligned 32-bit word that holds the byte (no blocking load in the gather)
+            for (int r = tid; r < rows; r += nthr) {
+              const uint8_t* a = src + src_of[s0 + r];
+              cp_async4(st + 4 * (size_t)r, a - ((uintptr_t)a & 3));
+            }
           } else {
             for (int r = tid; r < rows; r += nthr) st[r] = src[src_of[s0 + r]];
           }
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(REROOT2_THREADS) k_reroot_bulk(const __grid_co
             }
           }
         }
-        off += align16((size_t)rpc * rb);
+        off += align16((size_t)rpc * P.tab[t].pad);  // (pad = staged bytes per row)
       }
     }
     if (s0 == 0) TZ_RSTAMP(4);
@@ -670,6 +676,9 @@ __global__ void __launch_bounds__(REROOT2_THREADS) k_reroot_bulk(const __grid_co
             else if (e.y <= -2) e.y = -(trans[-(e.y + 2)] + 2);
             reinterpret_cast<int2*>(dst)[i] = e;
           }
+        } else if (P.tab[t].unit == 5) {  // one-byte rows staged as the words that hold them
+          const uint8_t* const srcb = P.tab[t].base + (size_t)b * N;
+          for (int r = tid; r < rows; r += nthr) dst[r] = st[4 * (size_t)r + ((uintptr_t)(srcb + src_of[s0 + r]) & 3)];
         } else if (P.tab[t].unit == 0) {  // opaque rows that came in by bulk copies go out as ONE bulk copy
           if (tid == 0) {
             fence_async_smem();
@@ -683,7 +692,7 @@ __global__ void __launch_bounds__(REROOT2_THREADS) k_reroot_bulk(const __grid_co
         } else {
           for (size_t i = tid; i < nbytes; i += nthr) dst[i] = st[i];
         }
-        off += align16((size_t)rpc * rb);
+        off += align16((size_t)rpc * P.tab[t].pad);
       }
       if (stored_bulk) {  // (thread 0) the staging area may be overwritten once the bulk stores have READ it
         bulk_commit();
@@ -775,45 +784,78 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
   }
   int64_t row_total = 0;
   for (int k = 0; k < nt; ++k) row_total += P.tab[k].kind >= 4 ? 0 : P.tab[k].rb;
-  // staging area: as large as lets every tree of the batch be resident at once (one wave over the 148 SMs), within
-  // [16 KB, 64 KB]; the index scratch (8 N bytes) and 1 KB of per-CTA reserve come on top
+  for (int k = 0; k < nt; ++k) P.tab[k].pad = (uint32_t)P.tab[k].rb;  // staged bytes per row
+  // TZ_REROOT_IMPL=ldgsts selects the previous gather (per-thread LDGSTS copies) for A/B measurements; default: bulk copies
+  static const bool use_ldgsts = [] {
+    const char* e = getenv("TZ_REROOT_IMPL");
+    return e != nullptr && strcmp(e, "ldgsts") == 0;
+  }();
   const int64_t per_sm = 227 * 1024;
+  if (!use_ldgsts) {
+    // ---- k_reroot_bulk -----------------------------------------------------------------------------------------------
+    int64_t bulk_bytes = 0, row_total = 0;
+    for (int k = 0; k < nt; ++k) {
+      RerootTab& tb = P.tab[k];
+      if (tb.kind == 4) P.p_tab = k;
+      if (tb.kind == 5) P.e_tab = k;
+      if (tb.kind >= 4) continue;
+      const bool aligned = (((uintptr_t)tb.base | (uintptr_t)tb.rb) & 15) == 0;
+      if ((tb.kind == 3 || tb.kind == 0) && aligned && tb.rb >= 16 && tb.rb < (1 << 20)) {
+        tb.unit = 0;  // moved by cp.async.bulk
+        bulk_bytes += tb.rb;
+      } else if (tb.kind == 0 && tb.rb == 1) {
+        tb.unit = 5;  // one-byte rows travel as the aligned word that holds them
+        tb.pad = 4;
+      }
+      row_total += tb.pad;
+    }
+    P.bulk_row_bytes = (int32_t)bulk_bytes;
+    // Staging area: as many CTAs per SM as let every tree of the batch be resident at once (one wave over the 148 SMs, at most
+    // 7) -- unless a chunk would then hold fewer than 8 destination rows (wide rows: go_9x9's are 5.4 KB): every chunk costs a
+    // memory round trip, two barriers and a pass over the table list, so fewer, larger CTAs (and several waves) move more
+    // bytes per second.  Measured on the go_9x9 shape: 3 rows per chunk at 7 CTAs per SM = 2.4 TB/s (profiles/r2d).
+    int ctas = (t->B + 147) / 148;
+    ctas = ctas < 1 ? 1 : (ctas > 7 ? 7 : ctas);
+    auto stage_for = [&](int c) {
+      int64_t st = per_sm / c - 1024 - 8 * (int64_t)t->N - 64;
+      st = st > 160 * 1024 ? 160 * 1024 : st;
+      return st & ~(int64_t)15;
+    };
+    while (ctas > 2 && (stage_for(ctas) - 16 * nt) / row_total < 8) --ctas;
+    const int64_t stage = stage_for(ctas);
+    int64_t rpc = stage > 0 ? (stage - 16 * nt) / row_total : 0;
+    // the mbarrier's transaction count is 20 bits: a chunk's bulk bytes stay below 1 MiB (the staging area is <= 160 KB)
+    if (rpc >= 1) {
+      P.stage_bytes = (int32_t)stage;
+      P.rpc = (int32_t)(rpc > t->N ? t->N : rpc);
+      const size_t smem = (size_t)stage + 8 * (size_t)t->N;
+      const bool big = ctas <= 3;  // few CTAs per SM: 512 threads each (pointer jumping and the scan over up to N nodes, the scatter)
+      auto kernel = big ? k_reroot_bulk<512> : k_reroot_bulk<128>;
+      if (smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+      }
+      kernel<<<t->B, big ? 512 : 128, smem, (cudaStream_t)stream>>>(P, action, reset_flag, persist_tree);
+      return launch_status();
+    }
+    for (int k = 0; k < nt; ++k) {  // (fall through to the one-table-at-a-time kernel below with the original descriptors)
+      P.tab[k].pad = (uint32_t)P.tab[k].rb;
+    }
+  }
+  int64_t row_total = 0;
+  for (int k = 0; k < nt; ++k) row_total += P.tab[k].kind >= 4 ? 0 : P.tab[k].rb;
+  // k_reroot_all: staging area as large as lets every tree of the batch be resident at once (one wave over the 148 SMs), within
+  // [16 KB, 64 KB]; the index scratch (8 N bytes) and 1 KB of per-CTA reserve come on top
   const int ctas_wanted = (t->B + 147) / 148;
   int64_t stage = per_sm / (ctas_wanted < 1 ? 1 : ctas_wanted) - 1024 - 8 * (int64_t)t->N - 64;
   stage = stage > 64 * 1024 ? 64 * 1024 : stage;
   stage = stage < 16 * 1024 ? 16 * 1024 : stage;
   stage &= ~(int64_t)15;
   const int64_t rpc = (stage - 16 * nt) / row_total;
-  if (rpc >= 1 && stage + 8 * (int64_t)t->N <= 200 * 1024) {
+  if (use_ldgsts && rpc >= 1 && stage + 8 * (int64_t)t->N <= 200 * 1024) {
     P.stage_bytes = (int32_t)stage;
     P.rpc = (int32_t)(rpc > t->N ? t->N : rpc);
     const size_t smem = (size_t)stage + 8 * (size_t)t->N;
-    // TZ_REROOT_IMPL=ldgsts selects the previous gather (per-thread LDGSTS copies) for A/B measurements; default: bulk copies
-    static const bool use_ldgsts = [] {
-      const char* e = getenv("TZ_REROOT_IMPL");
-      return e != nullptr && strcmp(e, "ldgsts") == 0;
-    }();
-    if (!use_ldgsts) {
-      int64_t bulk_bytes = 0;
-      for (int k = 0; k < nt; ++k) {
-        RerootTab& tb = P.tab[k];
-        if (tb.kind == 4) P.p_tab = k;
-        if (tb.kind == 5) P.e_tab = k;
-        const bool aligned = (((uintptr_t)tb.base | (uintptr_t)tb.rb) & 15) == 0;
-        if ((tb.kind == 3 || tb.kind == 0) && aligned && tb.rb >= 16 && tb.rb < (1 << 20)) {
-          tb.unit = 0;  // moved by cp.async.bulk
-          bulk_bytes += tb.rb;
-        }
-      }
-      // the mbarrier's transaction count is 20 bits: a chunk's bulk bytes must stay below 1 MiB (they do: the staging area is <= 64 KB)
-      P.bulk_row_bytes = (int32_t)bulk_bytes;
-      if (smem > 48 * 1024) {
-        const cudaError_t e = cudaFuncSetAttribute(k_reroot_bulk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return (int)e;
-      }
-      k_reroot_bulk<<<t->B, REROOT2_THREADS, smem, (cudaStream_t)stream>>>(P, action, reset_flag, persist_tree);
-      return launch_status();
-    }
     if (smem > 48 * 1024) {
       const cudaError_t e = cudaFuncSetAttribute(k_reroot_all, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return (int)e;

@@ -88,14 +88,16 @@ __device__ __forceinline__ void block_copy2(void* d0, const void* s0, void* d1, 
 
 // CTAs per SM the register budget is capped for: every tree of a ~1 K-tree batch resident at once (7 x 148 = 1036 CTAs of four
 // warps at <= 73 registers; two waves cost more than the spills)
-// (trees with more than 128 actions hold 8-16 register chunks per lane: no cap there, the spills cost more)
-template <int NC, int W>
+// (trees with more than 128 actions hold 8-16 register chunks per lane: no cap there, the spills cost more; the weighted
+// backup is one warp's dependent chain of exp / division sequences per level: capped at 128 registers it is 20 % faster than
+// at 72, measured on the othello shape -- profiles/r2e_ab.log vs r2c_warps.log)
+template <int NC, bool WEIGHTED, int W>
 struct WideOcc {
-  static constexpr int MIN_CTAS = NC > 4 ? 1 : (W == 2 ? 14 : (W == 4 ? 7 : 3));
+  static constexpr int MIN_CTAS = NC > 4 ? 1 : (WEIGHTED ? (W == 2 ? 8 : (W == 4 ? 4 : 2)) : (W == 2 ? 14 : (W == 4 ? 7 : 3)));
 };
 
 template <int NC, bool WEIGHTED, int SEL, int W>
-__global__ void __launch_bounds__(32 * W, WideOcc<NC, W>::MIN_CTAS) k_sim_wide(const __grid_constant__ SimP P, const __grid_constant__ SimLeafExtra X) {
+__global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_sim_wide(const __grid_constant__ SimP P, const __grid_constant__ SimLeafExtra X) {
   constexpr int NT = 32 * W;
   constexpr int WIN = NT;  // path levels per pass
   __shared__ int2 s_rec[WIN];    // {node, action taken there} of the pass's levels; index j <-> level lo + j
@@ -237,9 +239,8 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, W>::MIN_CTAS) k_sim_wide(c
         qd = tv.q[rec.x];
         nd = tv.n[rec.x];
         if (WEIGHTED) rd = tv.r[rec.x];
-        // warm L2 with the level's child_stats row: the scoring warps reach it one (or several) selector calls later
-        const char* rowp = reinterpret_cast<const char*>(tv.cs + (unsigned)rec.x * (unsigned)F);
-        for (int off = 0; off < 16 * F + 112; off += 128) prefetch_l2(rowp + off);
+        // (prefetching the level's child_stats row into L2 here was measured 3 % SLOWER on the go_9x9 shape and neutral on
+        // othello: a selector call is bound by its own ~370 dependent instructions, not by the row's latency -- r2e_ab.log)
       }
       float q_e = 0.0f;
       int n_e = 0;
@@ -322,6 +323,7 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, W>::MIN_CTAS) k_sim_wide(c
           bn = nX + 1;
           row = nxt;
         }
+        if (first_pass) TZ_WSTAMP(7);
       }
       if (scorer) {
         for (; j >= 0; j -= SW) {
@@ -527,6 +529,9 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, W>::MIN_CTAS) k_sim_wide(c
     block_copy2(lf.parent_out + (size_t)b * lf.rb, src, fresh_node >= 0 ? tbl + (size_t)fresh_node * lf.rb : nullptr, fresh, lf.rb, tid, NT);
   }
   TZ_WSTAMP(6);
+#ifdef TZ_PROFILE
+  if (tid == 0 && b < 4096) g_prof_gt[16 * b + 8] = L;
+#endif
   if (warp == 0) tl_max(P.tl_row, 2, lane);
 }
 
