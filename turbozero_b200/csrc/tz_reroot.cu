@@ -782,8 +782,6 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
     tb.magic = (exact && tb.units > 1) ? (uint32_t)(0x100000000ull / tb.units) + 1u : 0u;
     tb.pad = 0;
   }
-  int64_t row_total = 0;
-  for (int k = 0; k < nt; ++k) row_total += P.tab[k].kind >= 4 ? 0 : P.tab[k].rb;
   for (int k = 0; k < nt; ++k) P.tab[k].pad = (uint32_t)P.tab[k].rb;  // staged bytes per row
   // TZ_REROOT_IMPL=ldgsts selects the previous gather (per-thread LDGSTS copies) for A/B measurements; default: bulk copies
   static const bool use_ldgsts = [] {
