@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
                                                                const uint8_t* __restrict__ reset_flag, const int persist_tree) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ int wsum[NTHR / 32];
-  __shared__ __align__(8) uint64_t bar;
+  __shared__ __align__(8) uint64_t bars[2];  // one per staging buffer
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   constexpr int nthr = NTHR;
@@ -502,7 +502,10 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   // edge_map[ROOT, action]; -1 -> nothing retained (tree.py:201-203).  Out-of-range actions clamp like an XLA gather.
   const int c = do_reset ? -1 : P.edge[(size_t)b * N * F + min(max(action[b], 0), F - 1)];
   int count = 0;
-  if (tid == 0) mbar_init(&bar, 1);
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+  }
   TZ_RSTAMP(1);
   if (c >= 0) {
     // (1) ancestor test by pointer jumping (see k_reroot): Jacobi rounds between the two index arrays
@@ -565,142 +568,158 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   }
   TZ_RSTAMP(3);
   // (3) move rows, translate indices (tree.py:234-268): all tables per chunk of destination rows
-  const int rpc = P.rpc;
-  unsigned parity = 0;
+  // Two staging buffers: chunk k+1 is gathered (bulk copies / LDGSTS in flight) while chunk k is scattered, so reads and writes
+  // overlap inside a CTA instead of alternating.  Safe in place: the source rows of chunk k+1 lie above every destination row of
+  // chunks <= k (src_of[s] > s, chunks in increasing s).
+  const int rpc = P.rpc;  // destination rows per chunk = per buffer
+  uint8_t* const stage_buf[2] = {stage, stage + P.stage_bytes / 2};
 #ifdef TZ_PROFILE
   long long acc_issue = 0, acc_wait = 0, acc_scatter = 0, t_a = prof_gtime();
 #endif
-  for (int s0 = 0; s0 < count; s0 += rpc) {
-    const int rows = min(rpc, count - s0);
+  auto issue = [&](const int s0, const int rows, uint8_t* const stg, uint64_t* const barp) {
     // ---- gather --------------------------------------------------------------------------------------------------
-    if (tid == 0) mbar_expect_tx(&bar, (unsigned)rows * (unsigned)P.bulk_row_bytes);  // arms this chunk's phase
-    {
-      size_t off = 0;
-      for (int t = 0; t < P.ntab; ++t) {
-        const int kind = P.tab[t].kind;
-        if (kind >= 4) continue;  // p / edge_map: carried by the child_stats rows
-        const int64_t rb = P.tab[t].rb;
-        const uint8_t* const src = P.tab[t].base + (size_t)b * N * rb;
-        uint8_t* const st = stage + off;
-        const uint32_t unit = P.tab[t].unit, units = P.tab[t].units, magic = P.tab[t].magic;
-        if (unit == 0) {  // one bulk copy per row, one issuing thread per row
-          for (int r = tid; r < rows; r += nthr)
-            bulk_g2s(st + (size_t)r * rb, src + (size_t)src_of[s0 + r] * rb, (unsigned)rb, &bar);
-        } else if (units == 1) {  // narrow tables: one copy per row, no (row, unit) split
-          if (unit == 8) {
-            for (int r = tid; r < rows; r += nthr) cp_async8(st + 8 * (size_t)r, src + 8 * (size_t)src_of[s0 + r]);
-          } else if (unit == 4) {
-            for (int r = tid; r < rows; r += nthr) cp_async4(st + 4 * (size_t)r, src + 4 * (size_t)src_of[s0 + r]);
-          } else if (unit == 16) {
-            for (int r = tid; r < rows; r += nthr) cp_async16(st + 16 * (size_t)r, src + 16 * (size_t)src_of[s0 + r]);
-          } else if (unit == 5) {  // one-byte rows: the aligned 32-bit word that holds the byte (no blocking load in the gather)
-            for (int r = tid; r < rows; r += nthr) {
-              const uint8_t* a = src + src_of[s0 + r];
-              cp_async4(st + 4 * (size_t)r, a - ((uintptr_t)a & 3));
-            }
-          } else {
-            for (int r = tid; r < rows; r += nthr) st[r] = src[src_of[s0 + r]];
+  if (tid == 0) mbar_expect_tx(barp, (unsigned)rows * (unsigned)P.bulk_row_bytes);  // arms this chunk's phase
+  {
+    size_t off = 0;
+    for (int t = 0; t < P.ntab; ++t) {
+      const int kind = P.tab[t].kind;
+      if (kind >= 4) continue;  // p / edge_map: carried by the child_stats rows
+      const int64_t rb = P.tab[t].rb;
+      const uint8_t* const src = P.tab[t].base + (size_t)b * N * rb;
+      uint8_t* const st = stg + off;
+      const uint32_t unit = P.tab[t].unit, units = P.tab[t].units, magic = P.tab[t].magic;
+      if (unit == 0) {  // one bulk copy per row, one issuing thread per row
+        for (int r = tid; r < rows; r += nthr)
+          bulk_g2s(st + (size_t)r * rb, src + (size_t)src_of[s0 + r] * rb, (unsigned)rb, barp);
+      } else if (units == 1) {  // narrow tables: one copy per row, no (row, unit) split
+        if (unit == 8) {
+          for (int r = tid; r < rows; r += nthr) cp_async8(st + 8 * (size_t)r, src + 8 * (size_t)src_of[s0 + r]);
+        } else if (unit == 4) {
+          for (int r = tid; r < rows; r += nthr) cp_async4(st + 4 * (size_t)r, src + 4 * (size_t)src_of[s0 + r]);
+        } else if (unit == 16) {
+          for (int r = tid; r < rows; r += nthr) cp_async16(st + 16 * (size_t)r, src + 16 * (size_t)src_of[s0 + r]);
+        } else if (unit == 5) {  // one-byte rows: the aligned 32-bit word that holds the byte (no blocking load in the gather)
+          for (int r = tid; r < rows; r += nthr) {
+            const uint8_t* a = src + src_of[s0 + r];
+            cp_async4(st + 4 * (size_t)r, a - ((uintptr_t)a & 3));
           }
         } else {
-          const uint32_t total = (uint32_t)rows * units;
-          if (unit == 16) {
-            for (uint32_t i = tid; i < total; i += nthr) {
-              const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
-              cp_async16(st + (size_t)r * rb + 16 * u, src + (size_t)src_of[s0 + r] * rb + 16 * u);
-            }
-          } else if (unit == 8) {
-            for (uint32_t i = tid; i < total; i += nthr) {
-              const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
-              cp_async8(st + (size_t)r * rb + 8 * u, src + (size_t)src_of[s0 + r] * rb + 8 * u);
-            }
-          } else if (unit == 4) {
-            for (uint32_t i = tid; i < total; i += nthr) {
-              const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
-              cp_async4(st + (size_t)r * rb + 4 * u, src + (size_t)src_of[s0 + r] * rb + 4 * u);
-            }
-          } else {  // odd row sizes (bool / byte leaves): ordinary loads; the host orders these tables last
-            for (uint32_t i = tid; i < total; i += nthr) {
-              const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
-              st[i] = src[(size_t)src_of[s0 + r] * rb + u];
-            }
+          for (int r = tid; r < rows; r += nthr) st[r] = src[src_of[s0 + r]];
+        }
+      } else {
+        const uint32_t total = (uint32_t)rows * units;
+        if (unit == 16) {
+          for (uint32_t i = tid; i < total; i += nthr) {
+            const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
+            cp_async16(st + (size_t)r * rb + 16 * u, src + (size_t)src_of[s0 + r] * rb + 16 * u);
+          }
+        } else if (unit == 8) {
+          for (uint32_t i = tid; i < total; i += nthr) {
+            const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
+            cp_async8(st + (size_t)r * rb + 8 * u, src + (size_t)src_of[s0 + r] * rb + 8 * u);
+          }
+        } else if (unit == 4) {
+          for (uint32_t i = tid; i < total; i += nthr) {
+            const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
+            cp_async4(st + (size_t)r * rb + 4 * u, src + (size_t)src_of[s0 + r] * rb + 4 * u);
+          }
+        } else {  // odd row sizes (bool / byte leaves): ordinary loads; the host orders these tables last
+          for (uint32_t i = tid; i < total; i += nthr) {
+            const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
+            st[i] = src[(size_t)src_of[s0 + r] * rb + u];
           }
         }
-        off += align16((size_t)rpc * P.tab[t].pad);  // (pad = staged bytes per row)
       }
+      off += align16((size_t)rpc * P.tab[t].pad);  // (pad = staged bytes per row)
     }
-    if (s0 == 0) TZ_RSTAMP(4);
+  }
+    asm volatile("cp.async.commit_group;" ::: "memory");  // this chunk's LDGSTS copies are one group
+  };
+  auto scatter = [&](const int s0, const int rows, const uint8_t* const stg) {
+    // ---- scatter: the chunk's destination rows are contiguous in every table -----------------------------------------
+  {
+    size_t off = 0;
+    bool stored_bulk = false;
+    for (int t = 0; t < P.ntab; ++t) {
+      const int64_t rb = P.tab[t].rb;
+      const int kind = P.tab[t].kind;
+      if (kind >= 4) continue;  // written together with child_stats below
+      uint8_t* const dst = P.tab[t].base + ((size_t)b * N + (size_t)s0) * rb;
+      const uint8_t* const st = stg + off;
+      const size_t nbytes = (size_t)rows * rb;
+      if (kind == 3) {
+        // child_stats entries {q, n, p, edge}: one read of the staged entry -> the translated entry, the p word and the
+        // translated edge_map word (tables P.p_tab / P.e_tab)
+        int32_t* const p_dst = reinterpret_cast<int32_t*>(P.tab[P.p_tab].base) + ((size_t)b * N + (size_t)s0) * F;
+        int32_t* const e_dst = reinterpret_cast<int32_t*>(P.tab[P.e_tab].base) + ((size_t)b * N + (size_t)s0) * F;
+        const int n_ent = rows * F;
+        for (int i = tid; i < n_ent; i += nthr) {
+          int4 e = reinterpret_cast<const int4*>(st)[i];
+          e.w = e.w < 0 ? -1 : trans[e.w];  // tree.py:247-257
+          reinterpret_cast<int4*>(dst)[i] = e;
+          p_dst[i] = e.z;
+          e_dst[i] = e.w;
+        }
+      } else if (kind == 1) {  // every word is a node index (parents): tree.py:247-257
+        for (size_t i = tid; i < (nbytes >> 2); i += nthr) {
+          const int32_t x = reinterpret_cast<const int32_t*>(st)[i];
+          reinterpret_cast<int32_t*>(dst)[i] = x < 0 ? -1 : trans[x];
+        }
+      } else if (kind == 2) {  // best-table entries {action, next}: only `next` is an index (TzTree.best encoding)
+        for (size_t i = tid; i < (nbytes >> 3); i += nthr) {
+          int2 e = reinterpret_cast<const int2*>(st)[i];
+          if (e.y >= 0) e.y = trans[e.y];
+          else if (e.y <= -2) e.y = -(trans[-(e.y + 2)] + 2);
+          reinterpret_cast<int2*>(dst)[i] = e;
+        }
+      } else if (P.tab[t].unit == 5) {  // one-byte rows staged as the words that hold them
+        const uint8_t* const srcb = P.tab[t].base + (size_t)b * N;
+        for (int r = tid; r < rows; r += nthr) dst[r] = st[4 * (size_t)r + ((uintptr_t)(srcb + src_of[s0 + r]) & 3)];
+      } else if (P.tab[t].unit == 0) {  // opaque rows that came in by bulk copies go out as ONE bulk copy
+        if (tid == 0) {
+          fence_async_smem();
+          bulk_s2g(dst, st, (unsigned)nbytes);
+          stored_bulk = true;
+        }
+      } else if ((((uintptr_t)dst | nbytes) & 15) == 0) {
+        for (size_t i = tid; i < (nbytes >> 4); i += nthr) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(st)[i];
+      } else if ((((uintptr_t)dst | nbytes) & 3) == 0) {
+        for (size_t i = tid; i < (nbytes >> 2); i += nthr) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(st)[i];
+      } else {
+        for (size_t i = tid; i < nbytes; i += nthr) dst[i] = st[i];
+      }
+      off += align16((size_t)rpc * P.tab[t].pad);
+    }
+    if (stored_bulk) {  // (thread 0) the staging area may be overwritten once the bulk stores have READ it
+      bulk_commit();
+      bulk_wait_read0();
+    }
+  }
+  };
+  const int nchunks = (count + rpc - 1) / rpc;
+  if (nchunks > 0) issue(0, min(rpc, count), stage_buf[0], &bars[0]);
+  for (int kc = 0; kc < nchunks; ++kc) {
+    const int s0 = kc * rpc;
+    const int rows = min(rpc, count - s0);
+    if (kc + 1 < nchunks) {  // (its buffer was released by the barrier that ended iteration kc - 1)
+      issue(s0 + rpc, min(rpc, count - s0 - rpc), stage_buf[(kc + 1) & 1], &bars[(kc + 1) & 1]);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the group just issued: chunk kc has landed
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    if (kc == 0) TZ_RSTAMP(4);
 #ifdef TZ_PROFILE
     { const long long t_b = prof_gtime(); acc_issue += t_b - t_a; t_a = t_b; }
 #endif
-    cp_async_wait_all();
-    mbar_wait(&bar, parity);
-    parity ^= 1u;
+    mbar_wait(&bars[kc & 1], (unsigned)(kc >> 1) & 1u);
     __syncthreads();
-    if (s0 == 0) TZ_RSTAMP(5);
+    if (kc == 0) TZ_RSTAMP(5);
 #ifdef TZ_PROFILE
     { const long long t_b = prof_gtime(); acc_wait += t_b - t_a; t_a = t_b; }
 #endif
-    // ---- scatter: the chunk's destination rows are contiguous in every table -----------------------------------------
-    {
-      size_t off = 0;
-      bool stored_bulk = false;
-      for (int t = 0; t < P.ntab; ++t) {
-        const int64_t rb = P.tab[t].rb;
-        const int kind = P.tab[t].kind;
-        if (kind >= 4) continue;  // written together with child_stats below
-        uint8_t* const dst = P.tab[t].base + ((size_t)b * N + (size_t)s0) * rb;
-        const uint8_t* const st = stage + off;
-        const size_t nbytes = (size_t)rows * rb;
-        if (kind == 3) {
-          // child_stats entries {q, n, p, edge}: one read of the staged entry -> the translated entry, the p word and the
-          // translated edge_map word (tables P.p_tab / P.e_tab)
-          int32_t* const p_dst = reinterpret_cast<int32_t*>(P.tab[P.p_tab].base) + ((size_t)b * N + (size_t)s0) * F;
-          int32_t* const e_dst = reinterpret_cast<int32_t*>(P.tab[P.e_tab].base) + ((size_t)b * N + (size_t)s0) * F;
-          const int n_ent = rows * F;
-          for (int i = tid; i < n_ent; i += nthr) {
-            int4 e = reinterpret_cast<const int4*>(st)[i];
-            e.w = e.w < 0 ? -1 : trans[e.w];  // tree.py:247-257
-            reinterpret_cast<int4*>(dst)[i] = e;
-            p_dst[i] = e.z;
-            e_dst[i] = e.w;
-          }
-        } else if (kind == 1) {  // every word is a node index (parents): tree.py:247-257
-          for (size_t i = tid; i < (nbytes >> 2); i += nthr) {
-            const int32_t x = reinterpret_cast<const int32_t*>(st)[i];
-            reinterpret_cast<int32_t*>(dst)[i] = x < 0 ? -1 : trans[x];
-          }
-        } else if (kind == 2) {  // best-table entries {action, next}: only `next` is an index (TzTree.best encoding)
-          for (size_t i = tid; i < (nbytes >> 3); i += nthr) {
-            int2 e = reinterpret_cast<const int2*>(st)[i];
-            if (e.y >= 0) e.y = trans[e.y];
-            else if (e.y <= -2) e.y = -(trans[-(e.y + 2)] + 2);
-            reinterpret_cast<int2*>(dst)[i] = e;
-          }
-        } else if (P.tab[t].unit == 5) {  // one-byte rows staged as the words that hold them
-          const uint8_t* const srcb = P.tab[t].base + (size_t)b * N;
-          for (int r = tid; r < rows; r += nthr) dst[r] = st[4 * (size_t)r + ((uintptr_t)(srcb + src_of[s0 + r]) & 3)];
-        } else if (P.tab[t].unit == 0) {  // opaque rows that came in by bulk copies go out as ONE bulk copy
-          if (tid == 0) {
-            fence_async_smem();
-            bulk_s2g(dst, st, (unsigned)nbytes);
-            stored_bulk = true;
-          }
-        } else if ((((uintptr_t)dst | nbytes) & 15) == 0) {
-          for (size_t i = tid; i < (nbytes >> 4); i += nthr) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(st)[i];
-        } else if ((((uintptr_t)dst | nbytes) & 3) == 0) {
-          for (size_t i = tid; i < (nbytes >> 2); i += nthr) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(st)[i];
-        } else {
-          for (size_t i = tid; i < nbytes; i += nthr) dst[i] = st[i];
-        }
-        off += align16((size_t)rpc * P.tab[t].pad);
-      }
-      if (stored_bulk) {  // (thread 0) the staging area may be overwritten once the bulk stores have READ it
-        bulk_commit();
-        bulk_wait_read0();
-      }
-    }
-    __syncthreads();  // the staging area is reused by the next chunk
-    if (s0 == 0) TZ_RSTAMP(6);
+    scatter(s0, rows, stage_buf[kc & 1]);
+    __syncthreads();  // the buffer is reused by chunk kc + 2
+    if (kc == 0) TZ_RSTAMP(6);
 #ifdef TZ_PROFILE
     { const long long t_b = prof_gtime(); acc_scatter += t_b - t_a; t_a = t_b; }
 #endif
@@ -819,9 +838,10 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
       st = st > 160 * 1024 ? 160 * 1024 : st;
       return st & ~(int64_t)15;
     };
-    while (ctas > 2 && (stage_for(ctas) - 16 * nt) / row_total < 8) --ctas;
-    const int64_t stage = stage_for(ctas);
-    int64_t rpc = stage > 0 ? (stage - 16 * nt) / row_total : 0;
+    // (two buffers of stage / 2 each: chunk k+1 is gathered while chunk k is scattered)
+    while (ctas > 2 && (stage_for(ctas) / 2 - 16 * nt) / row_total < 8) --ctas;
+    const int64_t stage = stage_for(ctas) & ~(int64_t)31;
+    int64_t rpc = stage > 0 ? (stage / 2 - 16 * nt) / row_total : 0;
     // the mbarrier's transaction count is 20 bits: a chunk's bulk bytes stay below 1 MiB (the staging area is <= 160 KB)
     if (rpc >= 1) {
       P.stage_bytes = (int32_t)stage;
