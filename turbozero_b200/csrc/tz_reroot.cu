@@ -479,12 +479,24 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #else
 #define TZ_RSTAMP(i) do { } while (0)
 #endif
+// how a table's rows travel in k_reroot_bulk (TabDesc.code)
+enum : uint32_t { TD_SKIP = 0, TD_BULK, TD_N4, TD_N8, TD_N16, TD_BYTE, TD_UNITS };
+struct __align__(16) TabDesc {
+  uint8_t* base;     // this tree's block of the table
+  uint32_t st_off;   // the table's offset in the staging area
+  uint32_t rb;       // row bytes
+  uint32_t code;     // TD_*
+  uint32_t kind;     // RerootTab.kind
+  uint32_t pad[2];
+};
+
 template <int NTHR>
 __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ RerootP P, const int32_t* __restrict__ action,
                                                                const uint8_t* __restrict__ reset_flag, const int persist_tree) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   __shared__ int wsum[NTHR / 32];
-  __shared__ __align__(8) uint64_t bars[2];  // one per staging buffer
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ TabDesc s_td[REROOT_MAX_TABS];
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   constexpr int nthr = NTHR;
@@ -502,9 +514,26 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   // edge_map[ROOT, action]; -1 -> nothing retained (tree.py:201-203).  Out-of-range actions clamp like an XLA gather.
   const int c = do_reset ? -1 : P.edge[(size_t)b * N * F + min(max(action[b], 0), F - 1)];
   int count = 0;
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
+  if (tid == 0) mbar_init(&bar, 1);
+  if (tid < P.ntab) {  // this tree's table descriptors (once per kernel; visible after the barriers below)
+    const RerootTab& tb = P.tab[tid];
+    TabDesc d;
+    d.base = tb.base + (size_t)b * N * tb.rb;
+    size_t off = 0;
+    for (int t = 0; t < tid; ++t)
+      if (P.tab[t].kind < 4) off += align16((size_t)P.rpc * P.tab[t].pad);  // (pad = staged bytes per row)
+    d.st_off = (uint32_t)off;
+    d.rb = (uint32_t)tb.rb;
+    d.kind = (uint32_t)tb.kind;
+    d.code = tb.kind >= 4 ? TD_SKIP
+             : tb.unit == 0 ? TD_BULK
+             : tb.unit == 5 ? TD_BYTE
+             : (tb.units == 1 && tb.unit == 4) ? TD_N4
+             : (tb.units == 1 && tb.unit == 8) ? TD_N8
+             : (tb.units == 1 && tb.unit == 16) ? TD_N16
+                                                : TD_UNITS;
+    d.pad[0] = d.pad[1] = 0;
+    s_td[tid] = d;
   }
   TZ_RSTAMP(1);
   if (c >= 0) {
@@ -567,159 +596,158 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
     atomicAdd(reinterpret_cast<unsigned long long*>(P.stats) + 4 * (size_t)b + 3, (unsigned long long)count);
   }
   TZ_RSTAMP(3);
-  // (3) move rows, translate indices (tree.py:234-268): all tables per chunk of destination rows
-  // Two staging buffers: chunk k+1 is gathered (bulk copies / LDGSTS in flight) while chunk k is scattered, so reads and writes
-  // overlap inside a CTA instead of alternating.  Safe in place: the source rows of chunk k+1 lie above every destination row of
-  // chunks <= k (src_of[s] > s, chunks in increasing s).
-  const int rpc = P.rpc;  // destination rows per chunk = per buffer
-  uint8_t* const stage_buf[2] = {stage, stage + P.stage_bytes / 2};
+  // (3) move rows, translate indices (tree.py:234-268): all tables per chunk of destination rows.  The per-table facts a chunk
+  // needs (this tree's block, the table's offset in the staging area, how its rows travel) are worked out ONCE into shared
+  // memory (s_td, below); per chunk every WARP then takes whole tables (lanes over the rows), so a thread interprets 2-3
+  // descriptors per chunk instead of walking the kernel-parameter table list (~5 us per chunk when every thread did).
+  const int rpc = P.rpc;
+  constexpr int nwarps = NTHR / 32;
+  const int warp = tid >> 5, lane = tid & 31;
+  const TabDesc* const cs_td = &s_td[0];  // child_stats is table 0 (the host orders it first)
+  unsigned parity = 0;
 #ifdef TZ_PROFILE
   long long acc_issue = 0, acc_wait = 0, acc_scatter = 0, t_a = prof_gtime();
 #endif
-  auto issue = [&](const int s0, const int rows, uint8_t* const stg, uint64_t* const barp) {
+  for (int s0 = 0; s0 < count; s0 += rpc) {
+    const int rows = min(rpc, count - s0);
     // ---- gather --------------------------------------------------------------------------------------------------
-  if (tid == 0) mbar_expect_tx(barp, (unsigned)rows * (unsigned)P.bulk_row_bytes);  // arms this chunk's phase
-  {
-    size_t off = 0;
-    for (int t = 0; t < P.ntab; ++t) {
-      const int kind = P.tab[t].kind;
-      if (kind >= 4) continue;  // p / edge_map: carried by the child_stats rows
-      const int64_t rb = P.tab[t].rb;
-      const uint8_t* const src = P.tab[t].base + (size_t)b * N * rb;
-      uint8_t* const st = stg + off;
-      const uint32_t unit = P.tab[t].unit, units = P.tab[t].units, magic = P.tab[t].magic;
-      if (unit == 0) {  // one bulk copy per row, one issuing thread per row
-        for (int r = tid; r < rows; r += nthr)
-          bulk_g2s(st + (size_t)r * rb, src + (size_t)src_of[s0 + r] * rb, (unsigned)rb, barp);
-      } else if (units == 1) {  // narrow tables: one copy per row, no (row, unit) split
-        if (unit == 8) {
-          for (int r = tid; r < rows; r += nthr) cp_async8(st + 8 * (size_t)r, src + 8 * (size_t)src_of[s0 + r]);
-        } else if (unit == 4) {
-          for (int r = tid; r < rows; r += nthr) cp_async4(st + 4 * (size_t)r, src + 4 * (size_t)src_of[s0 + r]);
-        } else if (unit == 16) {
-          for (int r = tid; r < rows; r += nthr) cp_async16(st + 16 * (size_t)r, src + 16 * (size_t)src_of[s0 + r]);
-        } else if (unit == 5) {  // one-byte rows: the aligned 32-bit word that holds the byte (no blocking load in the gather)
-          for (int r = tid; r < rows; r += nthr) {
-            const uint8_t* a = src + src_of[s0 + r];
+    if (tid == 0) mbar_expect_tx(&bar, (unsigned)rows * (unsigned)P.bulk_row_bytes);  // arms this chunk's phase
+    for (int g = warp; g < P.ntab; g += nwarps) {
+      const TabDesc d = s_td[g];
+      uint8_t* const st = stage + d.st_off;
+      const uint32_t rb = d.rb;
+      switch (d.code) {
+        case TD_BULK:  // one bulk copy per row
+          for (int r = lane; r < rows; r += 32) bulk_g2s(st + (size_t)r * rb, d.base + (size_t)src_of[s0 + r] * rb, rb, &bar);
+          break;
+        case TD_N4:
+          for (int r = lane; r < rows; r += 32) cp_async4(st + 4 * (size_t)r, d.base + 4 * (size_t)src_of[s0 + r]);
+          break;
+        case TD_N8:
+          for (int r = lane; r < rows; r += 32) cp_async8(st + 8 * (size_t)r, d.base + 8 * (size_t)src_of[s0 + r]);
+          break;
+        case TD_N16:
+          for (int r = lane; r < rows; r += 32) cp_async16(st + 16 * (size_t)r, d.base + 16 * (size_t)src_of[s0 + r]);
+          break;
+        case TD_BYTE:  // one-byte rows: the aligned 32-bit word that holds the byte (no blocking load in the gather)
+          for (int r = lane; r < rows; r += 32) {
+            const uint8_t* a = d.base + src_of[s0 + r];
             cp_async4(st + 4 * (size_t)r, a - ((uintptr_t)a & 3));
           }
-        } else {
-          for (int r = tid; r < rows; r += nthr) st[r] = src[src_of[s0 + r]];
+          break;
+        case TD_UNITS: {  // wider rows that are not 16-byte aligned: `unit`-byte copies (the table list has unit / units)
+          const uint32_t unit = P.tab[g].unit, units = P.tab[g].units, magic = P.tab[g].magic;
+          const uint32_t total = (uint32_t)rows * units;
+          for (uint32_t i = lane; i < total; i += 32) {
+            const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
+            uint8_t* const sp = st + (size_t)r * rb + unit * u;
+            const uint8_t* const gp = d.base + (size_t)src_of[s0 + r] * rb + unit * u;
+            if (unit == 16) cp_async16(sp, gp);
+            else if (unit == 8) cp_async8(sp, gp);
+            else if (unit == 4) cp_async4(sp, gp);
+            else *sp = *gp;  // odd row sizes (byte leaves): ordinary loads
+          }
+          break;
         }
-      } else {
-        const uint32_t total = (uint32_t)rows * units;
-        if (unit == 16) {
-          for (uint32_t i = tid; i < total; i += nthr) {
-            const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
-            cp_async16(st + (size_t)r * rb + 16 * u, src + (size_t)src_of[s0 + r] * rb + 16 * u);
-          }
-        } else if (unit == 8) {
-          for (uint32_t i = tid; i < total; i += nthr) {
-            const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
-            cp_async8(st + (size_t)r * rb + 8 * u, src + (size_t)src_of[s0 + r] * rb + 8 * u);
-          }
-        } else if (unit == 4) {
-          for (uint32_t i = tid; i < total; i += nthr) {
-            const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
-            cp_async4(st + (size_t)r * rb + 4 * u, src + (size_t)src_of[s0 + r] * rb + 4 * u);
-          }
-        } else {  // odd row sizes (bool / byte leaves): ordinary loads; the host orders these tables last
-          for (uint32_t i = tid; i < total; i += nthr) {
-            const uint32_t r = magic ? __umulhi(i, magic) : i / units, u = i - r * units;
-            st[i] = src[(size_t)src_of[s0 + r] * rb + u];
-          }
-        }
+        default:  // TD_SKIP: p / edge_map, carried by the child_stats rows
+          break;
       }
-      off += align16((size_t)rpc * P.tab[t].pad);  // (pad = staged bytes per row)
     }
-  }
-    asm volatile("cp.async.commit_group;" ::: "memory");  // this chunk's LDGSTS copies are one group
-  };
-  auto scatter = [&](const int s0, const int rows, const uint8_t* const stg) {
-    // ---- scatter: the chunk's destination rows are contiguous in every table -----------------------------------------
-  {
-    size_t off = 0;
-    bool stored_bulk = false;
-    for (int t = 0; t < P.ntab; ++t) {
-      const int64_t rb = P.tab[t].rb;
-      const int kind = P.tab[t].kind;
-      if (kind >= 4) continue;  // written together with child_stats below
-      uint8_t* const dst = P.tab[t].base + ((size_t)b * N + (size_t)s0) * rb;
-      const uint8_t* const st = stg + off;
-      const size_t nbytes = (size_t)rows * rb;
-      if (kind == 3) {
-        // child_stats entries {q, n, p, edge}: one read of the staged entry -> the translated entry, the p word and the
-        // translated edge_map word (tables P.p_tab / P.e_tab)
-        int32_t* const p_dst = reinterpret_cast<int32_t*>(P.tab[P.p_tab].base) + ((size_t)b * N + (size_t)s0) * F;
-        int32_t* const e_dst = reinterpret_cast<int32_t*>(P.tab[P.e_tab].base) + ((size_t)b * N + (size_t)s0) * F;
-        const int n_ent = rows * F;
-        for (int i = tid; i < n_ent; i += nthr) {
-          int4 e = reinterpret_cast<const int4*>(st)[i];
-          e.w = e.w < 0 ? -1 : trans[e.w];  // tree.py:247-257
-          reinterpret_cast<int4*>(dst)[i] = e;
-          p_dst[i] = e.z;
-          e_dst[i] = e.w;
-        }
-      } else if (kind == 1) {  // every word is a node index (parents): tree.py:247-257
-        for (size_t i = tid; i < (nbytes >> 2); i += nthr) {
-          const int32_t x = reinterpret_cast<const int32_t*>(st)[i];
-          reinterpret_cast<int32_t*>(dst)[i] = x < 0 ? -1 : trans[x];
-        }
-      } else if (kind == 2) {  // best-table entries {action, next}: only `next` is an index (TzTree.best encoding)
-        for (size_t i = tid; i < (nbytes >> 3); i += nthr) {
-          int2 e = reinterpret_cast<const int2*>(st)[i];
-          if (e.y >= 0) e.y = trans[e.y];
-          else if (e.y <= -2) e.y = -(trans[-(e.y + 2)] + 2);
-          reinterpret_cast<int2*>(dst)[i] = e;
-        }
-      } else if (P.tab[t].unit == 5) {  // one-byte rows staged as the words that hold them
-        const uint8_t* const srcb = P.tab[t].base + (size_t)b * N;
-        for (int r = tid; r < rows; r += nthr) dst[r] = st[4 * (size_t)r + ((uintptr_t)(srcb + src_of[s0 + r]) & 3)];
-      } else if (P.tab[t].unit == 0) {  // opaque rows that came in by bulk copies go out as ONE bulk copy
-        if (tid == 0) {
-          fence_async_smem();
-          bulk_s2g(dst, st, (unsigned)nbytes);
-          stored_bulk = true;
-        }
-      } else if ((((uintptr_t)dst | nbytes) & 15) == 0) {
-        for (size_t i = tid; i < (nbytes >> 4); i += nthr) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(st)[i];
-      } else if ((((uintptr_t)dst | nbytes) & 3) == 0) {
-        for (size_t i = tid; i < (nbytes >> 2); i += nthr) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(st)[i];
-      } else {
-        for (size_t i = tid; i < nbytes; i += nthr) dst[i] = st[i];
-      }
-      off += align16((size_t)rpc * P.tab[t].pad);
-    }
-    if (stored_bulk) {  // (thread 0) the staging area may be overwritten once the bulk stores have READ it
-      bulk_commit();
-      bulk_wait_read0();
-    }
-  }
-  };
-  const int nchunks = (count + rpc - 1) / rpc;
-  if (nchunks > 0) issue(0, min(rpc, count), stage_buf[0], &bars[0]);
-  for (int kc = 0; kc < nchunks; ++kc) {
-    const int s0 = kc * rpc;
-    const int rows = min(rpc, count - s0);
-    if (kc + 1 < nchunks) {  // (its buffer was released by the barrier that ended iteration kc - 1)
-      issue(s0 + rpc, min(rpc, count - s0 - rpc), stage_buf[(kc + 1) & 1], &bars[(kc + 1) & 1]);
-      asm volatile("cp.async.wait_group 1;" ::: "memory");  // everything but the group just issued: chunk kc has landed
-    } else {
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    }
-    if (kc == 0) TZ_RSTAMP(4);
+    if (s0 == 0) TZ_RSTAMP(4);
 #ifdef TZ_PROFILE
     { const long long t_b = prof_gtime(); acc_issue += t_b - t_a; t_a = t_b; }
 #endif
-    mbar_wait(&bars[kc & 1], (unsigned)(kc >> 1) & 1u);
+    cp_async_wait_all();
+    mbar_wait(&bar, parity);
+    parity ^= 1u;
     __syncthreads();
-    if (kc == 0) TZ_RSTAMP(5);
+    if (s0 == 0) TZ_RSTAMP(5);
 #ifdef TZ_PROFILE
     { const long long t_b = prof_gtime(); acc_wait += t_b - t_a; t_a = t_b; }
 #endif
-    scatter(s0, rows, stage_buf[kc & 1]);
-    __syncthreads();  // the buffer is reused by chunk kc + 2
-    if (kc == 0) TZ_RSTAMP(6);
+    // ---- scatter: the chunk's destination rows are contiguous in every table -----------------------------------------
+    {  // child_stats entries {q, n, p, edge}, all threads: one read of the staged entry -> the translated entry, the p word and
+       // the translated edge_map word (tree.py:247-257)
+      const int4* const st = reinterpret_cast<const int4*>(stage + cs_td->st_off);
+      int4* const dst = reinterpret_cast<int4*>(cs_td->base) + (size_t)s0 * F;
+      int32_t* const p_dst = reinterpret_cast<int32_t*>(s_td[P.p_tab].base) + (size_t)s0 * F;
+      int32_t* const e_dst = reinterpret_cast<int32_t*>(s_td[P.e_tab].base) + (size_t)s0 * F;
+      const int n_ent = rows * F;
+      for (int i = tid; i < n_ent; i += nthr) {
+        int4 e = st[i];
+        e.w = e.w < 0 ? -1 : trans[e.w];
+        dst[i] = e;
+        p_dst[i] = e.z;
+        e_dst[i] = e.w;
+      }
+    }
+    bool stored_bulk = false;
+    for (int g = 1 + warp; g < P.ntab; g += nwarps) {
+      const TabDesc d = s_td[g];
+      const uint8_t* const st = stage + d.st_off;
+      uint8_t* const dst = d.base + (size_t)s0 * d.rb;
+      switch (d.code) {
+        case TD_BULK:  // opaque rows that came in by bulk copies go out as ONE bulk copy
+          if (lane == 0) {
+            fence_async_smem();
+            bulk_s2g(dst, st, (unsigned)rows * d.rb);
+            stored_bulk = true;
+          }
+          break;
+        case TD_N4:
+          if (d.kind == 1) {  // a node index (parents): tree.py:247-257
+            for (int r = lane; r < rows; r += 32) {
+              const int32_t x = reinterpret_cast<const int32_t*>(st)[r];
+              reinterpret_cast<int32_t*>(dst)[r] = x < 0 ? -1 : trans[x];
+            }
+          } else {
+            for (int r = lane; r < rows; r += 32) reinterpret_cast<uint32_t*>(dst)[r] = reinterpret_cast<const uint32_t*>(st)[r];
+          }
+          break;
+        case TD_N8:
+          if (d.kind == 2) {  // best-table entries {action, next}: only `next` is an index (TzTree.best encoding)
+            for (int r = lane; r < rows; r += 32) {
+              int2 e = reinterpret_cast<const int2*>(st)[r];
+              if (e.y >= 0) e.y = trans[e.y];
+              else if (e.y <= -2) e.y = -(trans[-(e.y + 2)] + 2);
+              reinterpret_cast<int2*>(dst)[r] = e;
+            }
+          } else {
+            for (int r = lane; r < rows; r += 32) reinterpret_cast<uint2*>(dst)[r] = reinterpret_cast<const uint2*>(st)[r];
+          }
+          break;
+        case TD_N16:
+          for (int r = lane; r < rows; r += 32) reinterpret_cast<uint4*>(dst)[r] = reinterpret_cast<const uint4*>(st)[r];
+          break;
+        case TD_BYTE:  // one-byte rows staged as the words that hold them
+          for (int r = lane; r < rows; r += 32) dst[r] = st[4 * (size_t)r + ((uintptr_t)(d.base + src_of[s0 + r]) & 3)];
+          break;
+        case TD_UNITS: {
+          const size_t nbytes = (size_t)rows * d.rb;
+          if (d.kind == 1) {  // every word is a node index
+            for (size_t i = lane; i < (nbytes >> 2); i += 32) {
+              const int32_t x = reinterpret_cast<const int32_t*>(st)[i];
+              reinterpret_cast<int32_t*>(dst)[i] = x < 0 ? -1 : trans[x];
+            }
+          } else if ((((uintptr_t)dst | nbytes) & 15) == 0) {
+            for (size_t i = lane; i < (nbytes >> 4); i += 32) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(st)[i];
+          } else if ((((uintptr_t)dst | nbytes) & 3) == 0) {
+            for (size_t i = lane; i < (nbytes >> 2); i += 32) reinterpret_cast<uint32_t*>(dst)[i] = reinterpret_cast<const uint32_t*>(st)[i];
+          } else {
+            for (size_t i = lane; i < nbytes; i += 32) dst[i] = st[i];
+          }
+          break;
+        }
+        default:
+          break;
+      }
+    }
+    if (stored_bulk) {  // (the issuing lanes) the staging area may be overwritten once the bulk stores have READ it
+      bulk_commit();
+      bulk_wait_read0();
+    }
+    __syncthreads();  // the staging area is reused by the next chunk
+    if (s0 == 0) TZ_RSTAMP(6);
 #ifdef TZ_PROFILE
     { const long long t_b = prof_gtime(); acc_scatter += t_b - t_a; t_a = t_b; }
 #endif
@@ -838,10 +866,9 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
       st = st > 160 * 1024 ? 160 * 1024 : st;
       return st & ~(int64_t)15;
     };
-    // (two buffers of stage / 2 each: chunk k+1 is gathered while chunk k is scattered)
-    while (ctas > 2 && (stage_for(ctas) / 2 - 16 * nt) / row_total < 8) --ctas;
-    const int64_t stage = stage_for(ctas) & ~(int64_t)31;
-    int64_t rpc = stage > 0 ? (stage / 2 - 16 * nt) / row_total : 0;
+    while (ctas > 2 && (stage_for(ctas) - 16 * nt) / row_total < 8) --ctas;
+    const int64_t stage = stage_for(ctas);
+    int64_t rpc = stage > 0 ? (stage - 16 * nt) / row_total : 0;
     // the mbarrier's transaction count is 20 bits: a chunk's bulk bytes stay below 1 MiB (the staging area is <= 160 KB)
     if (rpc >= 1) {
       P.stage_bytes = (int32_t)stage;
