@@ -484,10 +484,9 @@ enum : uint32_t { TD_SKIP = 0, TD_BULK, TD_N4, TD_N8, TD_N16, TD_BYTE, TD_UNITS 
 struct __align__(16) TabDesc {
   uint8_t* base;     // this tree's block of the table
   uint32_t st_off;   // the table's offset in the staging area
-  uint32_t rb;       // row bytes
-  uint32_t code;     // TD_*
-  uint32_t kind;     // RerootTab.kind
-  uint32_t pad[2];
+  uint32_t rb : 24;  // row bytes (< 2^20: a row fits the staging area)
+  uint32_t code : 4; // TD_*
+  uint32_t kind : 4; // RerootTab.kind
 };
 
 template <int NTHR>
@@ -532,7 +531,6 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
              : (tb.units == 1 && tb.unit == 8) ? TD_N8
              : (tb.units == 1 && tb.unit == 16) ? TD_N16
                                                 : TD_UNITS;
-    d.pad[0] = d.pad[1] = 0;
     s_td[tid] = d;
   }
   TZ_RSTAMP(1);
@@ -845,7 +843,8 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
       if (tb.kind == 5) P.e_tab = k;
       if (tb.kind >= 4) continue;
       const bool aligned = (((uintptr_t)tb.base | (uintptr_t)tb.rb) & 15) == 0;
-      if ((tb.kind == 3 || tb.kind == 0) && aligned && tb.rb >= 16 && tb.rb < (1 << 20)) {
+      // (16-byte rows stay with one LDGSTS each: the bulk-copy unit takes ~4 cycles per copy whatever its size)
+      if ((tb.kind == 3 || tb.kind == 0) && aligned && tb.rb >= 32 && tb.rb < (1 << 20)) {
         tb.unit = 0;  // moved by cp.async.bulk
         bulk_bytes += tb.rb;
       } else if (tb.kind == 0 && tb.rb == 1) {
@@ -862,7 +861,7 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
     int ctas = (t->B + 147) / 148;
     ctas = ctas < 1 ? 1 : (ctas > 7 ? 7 : ctas);
     auto stage_for = [&](int c) {
-      int64_t st = per_sm / c - 1024 - 8 * (int64_t)t->N - 64;
+      int64_t st = per_sm / c - 1024 - 640 - 8 * (int64_t)t->N - 64;  // (1 KB per-CTA reserve, static shared memory, index scratch)
       st = st > 160 * 1024 ? 160 * 1024 : st;
       return st & ~(int64_t)15;
     };
