@@ -116,7 +116,10 @@ def build_jax_ffi() -> Path:
 
 
 if __name__ == "__main__":
-    if "--prof" in sys.argv:  # diagnostic build with in-kernel phase clocks: lib*_prof.so (scripts/phase_*.py, scripts/timeline.py)
+    if "--exp" in sys.argv:  # experiment builds: python -m turbozero_b200.build --exp _notl -DTZ_NO_TIMELINE  -> lib*_notl.so
+        i = sys.argv.index("--exp")
+        build(force=True, extra_flags=tuple(sys.argv[i + 2:]), suffix=sys.argv[i + 1])
+    elif "--prof" in sys.argv:  # diagnostic build with in-kernel phase clocks: lib*_prof.so (scripts/phase_*.py, scripts/timeline.py)
         build(force="--force" in sys.argv, verbose="-v" in sys.argv, extra_flags=("-DTZ_PROFILE", "-rdc=true"), suffix="_prof")
     else:
         build(force="--force" in sys.argv, verbose="-v" in sys.argv)

@@ -480,7 +480,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 #define TZ_RSTAMP(i) do { } while (0)
 #endif
 // how a table's rows travel in k_reroot_bulk (TabDesc.code)
-enum : uint32_t { TD_SKIP = 0, TD_BULK, TD_N4, TD_N8, TD_N16, TD_BYTE, TD_UNITS };
+enum : uint32_t { TD_SKIP = 0, TD_BULK, TD_N4, TD_N8, TD_N16, TD_BYTE, TD_UNITS, TD_PRE };
 struct __align__(16) TabDesc {
   uint8_t* base;     // this tree's block of the table
   uint32_t st_off;   // the table's offset in the staging area
@@ -520,18 +520,31 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
     d.base = tb.base + (size_t)b * N * tb.rb;
     size_t off = 0;
     for (int t = 0; t < tid; ++t)
-      if (P.tab[t].kind < 4) off += align16((size_t)P.rpc * P.tab[t].pad);  // (pad = staged bytes per row)
-    d.st_off = (uint32_t)off;
+      if (P.tab[t].kind < 4 && P.tab[t].unit != 6) off += align16((size_t)P.rpc * P.tab[t].pad);  // (pad = staged bytes per row)
+    d.st_off = tb.unit == 6 ? tb.magic : (uint32_t)off;  // preloaded tables: offset in the preload area
     d.rb = (uint32_t)tb.rb;
     d.kind = (uint32_t)tb.kind;
     d.code = tb.kind >= 4 ? TD_SKIP
              : tb.unit == 0 ? TD_BULK
+             : tb.unit == 6 ? TD_PRE
              : tb.unit == 5 ? TD_BYTE
              : (tb.units == 1 && tb.unit == 4) ? TD_N4
              : (tb.units == 1 && tb.unit == 8) ? TD_N8
              : (tb.units == 1 && tb.unit == 16) ? TD_N16
                                                 : TD_UNITS;
     s_td[tid] = d;
+  }
+  // Narrow tables (4 / 8 / 1 bytes per row: best, parents, n, q, r, terminated) are not moved chunk by chunk: gathering them
+  // costs one memory transaction per row and table (the chunk gather was transaction-bound), while the WHOLE table of this
+  // tree is a few coalesced lines.  They are copied to shared memory here (fire-and-forget; they land during the ancestor test)
+  // and compacted from there once the translation is known.
+  uint8_t* const pre = reinterpret_cast<uint8_t*>(src_of + N);
+  for (int t = 0; t < P.ntab; ++t) {
+    if (P.tab[t].unit != 6) continue;
+    const uint8_t* const src = P.tab[t].base + (size_t)b * N * P.tab[t].rb;
+    uint8_t* const dstp = pre + P.tab[t].magic;
+    const int words = (int)(((size_t)nfi * P.tab[t].rb + 3) >> 2);
+    for (int i = tid; i < words; i += nthr) cp_async4(dstp + 4 * (size_t)i, src + 4 * (size_t)i);
   }
   TZ_RSTAMP(1);
   if (c >= 0) {
@@ -592,6 +605,42 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   if (tid == 0 && P.stats) {
     atomicAdd(reinterpret_cast<unsigned long long*>(P.stats) + 4 * (size_t)b + 2, (unsigned long long)nfi);
     atomicAdd(reinterpret_cast<unsigned long long*>(P.stats) + 4 * (size_t)b + 3, (unsigned long long)count);
+  }
+  // (2b) the preloaded narrow tables: new row s <- old row src_of[s], indices translated; rows [count, nfi) nulled
+  cp_async_wait_all();
+  __syncthreads();
+  for (int g = 0; g < P.ntab; ++g) {
+    const TabDesc d = s_td[g];
+    if (d.code != TD_PRE) continue;
+    const uint8_t* const sp = pre + d.st_off;
+    if (d.rb == 4) {
+      int32_t* const out = reinterpret_cast<int32_t*>(d.base);
+      const int32_t nullv = (int32_t)P.tab[g].null_pattern;
+      for (int sidx = tid; sidx < nfi; sidx += nthr) {
+        int32_t x = nullv;
+        if (sidx < count) {
+          x = reinterpret_cast<const int32_t*>(sp)[src_of[sidx]];
+          if (d.kind == 1) x = x < 0 ? -1 : trans[x];  // a node index (parents): tree.py:247-257
+        }
+        out[sidx] = x;
+      }
+    } else if (d.rb == 8) {
+      int2* const out = reinterpret_cast<int2*>(d.base);
+      const int32_t nullv = (int32_t)P.tab[g].null_pattern;
+      for (int sidx = tid; sidx < nfi; sidx += nthr) {
+        int2 e = make_int2(nullv, nullv);
+        if (sidx < count) {
+          e = reinterpret_cast<const int2*>(sp)[src_of[sidx]];
+          if (d.kind == 2) {  // best-table entries {action, next}: only `next` is an index (TzTree.best encoding)
+            if (e.y >= 0) e.y = trans[e.y];
+            else if (e.y <= -2) e.y = -(trans[-(e.y + 2)] + 2);
+          }
+        }
+        out[sidx] = e;
+      }
+    } else {  // one byte per row
+      for (int sidx = tid; sidx < nfi; sidx += nthr) d.base[sidx] = sidx < count ? sp[src_of[sidx]] : (uint8_t)P.tab[g].null_pattern;
+    }
   }
   TZ_RSTAMP(3);
   // (3) move rows, translate indices (tree.py:234-268): all tables per chunk of destination rows.  The per-table facts a chunk
@@ -753,6 +802,7 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   TZ_RSTAMP(7);
   // (4) null the tail rows [count, nfi) (tree.py:236-238,247-249): after every source row has been read
   for (int t = 0; t < P.ntab; ++t) {
+    if (P.tab[t].unit == 6) continue;  // preloaded narrow tables: done in (2b)
     const int64_t rb = P.tab[t].rb;
     uint8_t* const base = P.tab[t].base + (size_t)b * N * rb;
     if (P.tab[t].kind == 3) {
@@ -836,12 +886,24 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
   const int64_t per_sm = 227 * 1024;
   if (!use_ldgsts) {
     // ---- k_reroot_bulk -----------------------------------------------------------------------------------------------
-    int64_t bulk_bytes = 0, row_total = 0;
+    int64_t bulk_bytes = 0, row_total = 0, pre_bytes = 0;
+    // narrow tables are preloaded whole into shared memory when that costs little of it (N * 21 bytes: trees of <= 512 nodes)
+    int64_t narrow = 0;
+    for (int k = 0; k < nt; ++k)
+      if (P.tab[k].kind <= 2 && (P.tab[k].rb == 4 || P.tab[k].rb == 8 || P.tab[k].rb == 1)) narrow += (P.tab[k].rb * (int64_t)t->N + 15) & ~(int64_t)15;
+    const bool preload = narrow <= 12 * 1024 && (t->N & 3) == 0;
     for (int k = 0; k < nt; ++k) {
       RerootTab& tb = P.tab[k];
       if (tb.kind == 4) P.p_tab = k;
       if (tb.kind == 5) P.e_tab = k;
       if (tb.kind >= 4) continue;
+      if (preload && tb.kind <= 2 && (tb.rb == 4 || tb.rb == 8 || tb.rb == 1) && (((uintptr_t)tb.base) & 3) == 0) {
+        tb.unit = 6;  // copied whole to shared memory, compacted from there
+        tb.magic = (uint32_t)pre_bytes;
+        tb.pad = 0;
+        pre_bytes += (tb.rb * (int64_t)t->N + 15) & ~(int64_t)15;
+        continue;
+      }
       const bool aligned = (((uintptr_t)tb.base | (uintptr_t)tb.rb) & 15) == 0;
       // (16-byte rows stay with one LDGSTS each: the bulk-copy unit takes ~4 cycles per copy whatever its size)
       if ((tb.kind == 3 || tb.kind == 0) && aligned && tb.rb >= 32 && tb.rb < (1 << 20)) {
@@ -861,7 +923,7 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
     int ctas = (t->B + 147) / 148;
     ctas = ctas < 1 ? 1 : (ctas > 7 ? 7 : ctas);
     auto stage_for = [&](int c) {
-      int64_t st = per_sm / c - 1024 - 640 - 8 * (int64_t)t->N - 64;  // (1 KB per-CTA reserve, static shared memory, index scratch)
+      int64_t st = per_sm / c - 1024 - 640 - 8 * (int64_t)t->N - pre_bytes - 64;  // (1 KB per-CTA reserve, static shared memory, index scratch, preloaded tables)
       st = st > 160 * 1024 ? 160 * 1024 : st;
       return st & ~(int64_t)15;
     };
@@ -872,7 +934,7 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
     if (rpc >= 1) {
       P.stage_bytes = (int32_t)stage;
       P.rpc = (int32_t)(rpc > t->N ? t->N : rpc);
-      const size_t smem = (size_t)stage + 8 * (size_t)t->N;
+      const size_t smem = (size_t)stage + 8 * (size_t)t->N + (size_t)pre_bytes;
       const bool big = ctas <= 3;  // few CTAs per SM: 512 threads each (pointer jumping and the scan over up to N nodes, the scatter)
       auto kernel = big ? k_reroot_bulk<512> : k_reroot_bulk<128>;
       if (smem > 48 * 1024) {
