@@ -234,6 +234,8 @@ struct RerootTab {
   uint32_t units;  // rb / unit
   uint32_t magic;  // floor(2^32 / units) + 1: i / units == __umulhi(i, magic) for the index range of a chunk
   uint32_t pad;
+  uint32_t st_off; // k_reroot_bulk: the table's offset in the staging area (or, preloaded tables, in the preload area)
+  uint32_t code;   // k_reroot_bulk: TD_* (how the table's rows travel)
 };
 struct RerootP {
   int32_t B, N, F, ntab;
@@ -245,7 +247,7 @@ struct RerootP {
   int32_t rpc;          // destination rows per chunk (>= 1)
   int32_t bulk_row_bytes;  // k_reroot_bulk: bytes per destination row that arrive by bulk copies (sum of rb over unit == 0 tables)
   int32_t p_tab, e_tab;    // k_reroot_bulk: indices of the p / edge_map tables (kinds 4 / 5)
-  int32_t pad;
+  int32_t pre_first;       // k_reroot_bulk: tables [pre_first, ntab) are preloaded whole into shared memory
   RerootTab tab[REROOT_MAX_TABS];
 };
 
@@ -518,20 +520,10 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
     const RerootTab& tb = P.tab[tid];
     TabDesc d;
     d.base = tb.base + (size_t)b * N * tb.rb;
-    size_t off = 0;
-    for (int t = 0; t < tid; ++t)
-      if (P.tab[t].kind < 4 && P.tab[t].unit != 6) off += align16((size_t)P.rpc * P.tab[t].pad);  // (pad = staged bytes per row)
-    d.st_off = tb.unit == 6 ? tb.magic : (uint32_t)off;  // preloaded tables: offset in the preload area
+    d.st_off = tb.st_off;
     d.rb = (uint32_t)tb.rb;
     d.kind = (uint32_t)tb.kind;
-    d.code = tb.kind >= 4 ? TD_SKIP
-             : tb.unit == 0 ? TD_BULK
-             : tb.unit == 6 ? TD_PRE
-             : tb.unit == 5 ? TD_BYTE
-             : (tb.units == 1 && tb.unit == 4) ? TD_N4
-             : (tb.units == 1 && tb.unit == 8) ? TD_N8
-             : (tb.units == 1 && tb.unit == 16) ? TD_N16
-                                                : TD_UNITS;
+    d.code = tb.code;
     s_td[tid] = d;
   }
   // Narrow tables (4 / 8 / 1 bytes per row: best, parents, n, q, r, terminated) are not moved chunk by chunk: gathering them
@@ -539,10 +531,9 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   // tree is a few coalesced lines.  They are copied to shared memory here (fire-and-forget; they land during the ancestor test)
   // and compacted from there once the translation is known.
   uint8_t* const pre = reinterpret_cast<uint8_t*>(src_of + N);
-  for (int t = 0; t < P.ntab; ++t) {
-    if (P.tab[t].unit != 6) continue;
+  for (int t = P.pre_first; t < P.ntab; ++t) {  // (the host orders the preloaded tables last)
     const uint8_t* const src = P.tab[t].base + (size_t)b * N * P.tab[t].rb;
-    uint8_t* const dstp = pre + P.tab[t].magic;
+    uint8_t* const dstp = pre + P.tab[t].st_off;
     const int words = (int)(((size_t)nfi * P.tab[t].rb + 3) >> 2);
     for (int i = tid; i < words; i += nthr) cp_async4(dstp + 4 * (size_t)i, src + 4 * (size_t)i);
   }
@@ -609,9 +600,8 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   // (2b) the preloaded narrow tables: new row s <- old row src_of[s], indices translated; rows [count, nfi) nulled
   cp_async_wait_all();
   __syncthreads();
-  for (int g = 0; g < P.ntab; ++g) {
+  for (int g = P.pre_first; g < P.ntab; ++g) {
     const TabDesc d = s_td[g];
-    if (d.code != TD_PRE) continue;
     const uint8_t* const sp = pre + d.st_off;
     if (d.rb == 4) {
       int32_t* const out = reinterpret_cast<int32_t*>(d.base);
@@ -659,7 +649,7 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
     const int rows = min(rpc, count - s0);
     // ---- gather --------------------------------------------------------------------------------------------------
     if (tid == 0) mbar_expect_tx(&bar, (unsigned)rows * (unsigned)P.bulk_row_bytes);  // arms this chunk's phase
-    for (int g = warp; g < P.ntab; g += nwarps) {
+    for (int g = warp; g < P.pre_first; g += nwarps) {
       const TabDesc d = s_td[g];
       uint8_t* const st = stage + d.st_off;
       const uint32_t rb = d.rb;
@@ -729,7 +719,7 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
       }
     }
     bool stored_bulk = false;
-    for (int g = 1 + warp; g < P.ntab; g += nwarps) {
+    for (int g = 1 + warp; g < P.pre_first; g += nwarps) {
       const TabDesc d = s_td[g];
       const uint8_t* const st = stage + d.st_off;
       uint8_t* const dst = d.base + (size_t)s0 * d.rb;
@@ -801,8 +791,7 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   }
   TZ_RSTAMP(7);
   // (4) null the tail rows [count, nfi) (tree.py:236-238,247-249): after every source row has been read
-  for (int t = 0; t < P.ntab; ++t) {
-    if (P.tab[t].unit == 6) continue;  // preloaded narrow tables: done in (2b)
+  for (int t = 0; t < P.pre_first; ++t) {  // (the preloaded narrow tables were done in (2b))
     const int64_t rb = P.tab[t].rb;
     uint8_t* const base = P.tab[t].base + (size_t)b * N * rb;
     if (P.tab[t].kind == 3) {
@@ -915,6 +904,20 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
       }
       row_total += tb.pad;
     }
+    {  // preloaded tables last (stable), so that the kernel's loops need no per-table test
+      RerootTab tmp[REROOT_MAX_TABS];
+      int m = 0;
+      for (int k = 0; k < nt; ++k)
+        if (P.tab[k].unit != 6) tmp[m++] = P.tab[k];
+      P.pre_first = m;
+      for (int k = 0; k < nt; ++k)
+        if (P.tab[k].unit == 6) tmp[m++] = P.tab[k];
+      for (int k = 0; k < nt; ++k) {
+        P.tab[k] = tmp[k];
+        if (P.tab[k].kind == 4) P.p_tab = k;
+        if (P.tab[k].kind == 5) P.e_tab = k;
+      }
+    }
     P.bulk_row_bytes = (int32_t)bulk_bytes;
     // Staging area: as many CTAs per SM as let every tree of the batch be resident at once (one wave over the 148 SMs, at most
     // 7) -- unless a chunk would then hold fewer than 8 destination rows (wide rows: go_9x9's are 5.4 KB): every chunk costs a
@@ -934,6 +937,24 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
     if (rpc >= 1) {
       P.stage_bytes = (int32_t)stage;
       P.rpc = (int32_t)(rpc > t->N ? t->N : rpc);
+      size_t off = 0;
+      for (int k = 0; k < nt; ++k) {  // how every table's rows travel, and where they are staged
+        RerootTab& tb = P.tab[k];
+        if (tb.unit == 6) {
+          tb.st_off = tb.magic;
+          tb.code = TD_PRE;
+          continue;
+        }
+        tb.st_off = (uint32_t)off;
+        tb.code = tb.kind >= 4 ? TD_SKIP
+                  : tb.unit == 0 ? TD_BULK
+                  : tb.unit == 5 ? TD_BYTE
+                  : (tb.units == 1 && tb.unit == 4) ? TD_N4
+                  : (tb.units == 1 && tb.unit == 8) ? TD_N8
+                  : (tb.units == 1 && tb.unit == 16) ? TD_N16
+                                                     : TD_UNITS;
+        if (tb.kind < 4) off += ((size_t)P.rpc * tb.pad + 15) & ~(size_t)15;
+      }
       const size_t smem = (size_t)stage + 8 * (size_t)t->N + (size_t)pre_bytes;
       const bool big = ctas <= 3;  // few CTAs per SM: 512 threads each (pointer jumping and the scan over up to N nodes, the scatter)
       auto kernel = big ? k_reroot_bulk<512> : k_reroot_bulk<128>;
