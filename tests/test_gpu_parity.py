@@ -479,3 +479,19 @@ def test_cta_per_tree_at_bench_shapes():
     for warps in (0, 2):
         s = Schedule(game=SN.make_game("othello", 3002), B=512, N=400, S=200, moves=2, temperature=1.0, weighted=True, sim_warps=warps)
         _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), f"othello weighted, sim_warps={warps}")
+
+
+@pytest.mark.parametrize("name", ["puct_identity_qtransform", "muzero_puct_arityfix"])
+def test_registered_q_transforms_with_programmatic_launches(name):
+    """The identity q_transform is compiled for ordinary launches only: asking for programmatic launches with it must still
+    give the reference's trees (the library launches that shape ordinarily); normalize_q_values keeps the programmatic form."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden as MG
+
+    s, z = MG.load_case(name)
+    s.programmatic = True
+    for graph in (False, True):
+        res = run_cuda_selfplay(s, graph=graph)
+        assert np.array_equal(res.actions, z["actions"]) and np.array_equal(res.pw, z["pw"]), name
+        assert_trees_equal(MG.split(z, "final"), res.arrays, f"{name}: final trees, programmatic, graph={graph}")

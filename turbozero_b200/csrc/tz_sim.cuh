@@ -26,7 +26,7 @@ __global__ void __launch_bounds__(SIM_THREADS) k_sim(const __grid_constant__ Sim
 
   TZ_STAMP(0);
   TZ_TL_MIN(P.pad0, 0);
-  tl_min(P.tl_row, 0, lane);
+  if (mode & MODE_TIMELINE) tl_min(P.tl_row, 0, lane);
 #ifdef TZ_PROFILE
   const long long prof_t0 = prof_gtime();
 #endif
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(SIM_THREADS) k_sim(const __grid_constant__ Sim
       TZ_STAMP(1);
       if constexpr (pdl) load_leaf_results();
       TZ_TL_MAX(P.pad0, 1);
-      tl_max(P.tl_row, 1, lane);
+      if (mode & MODE_TIMELINE) tl_max(P.tl_row, 1, lane);
 
       // ---- expand: visit an existing (terminal) child, or add_node (mcts.py:174-187, tree.py:101-132) ------------
       const int node = exists ? end_child : (nfi < tv.N ? nfi : -1);  // full tree: nothing is written (tree.py:116-131)
@@ -471,7 +471,7 @@ __global__ void __launch_bounds__(SIM_THREADS) k_sim(const __grid_constant__ Sim
       if (k < SIM_LEAVES_INLINE && ((P.fast_mask >> k) & 1)) continue;
       move_leaf(k < SIM_LEAVES_INLINE ? P.leaf[k] : X.leaf[k - SIM_LEAVES_INLINE], b, tv.N, false, 0, fresh_node, lane);
     }
-    tl_max(P.tl_row, 2, lane);
+    if (mode & MODE_TIMELINE) tl_max(P.tl_row, 2, lane);
     return;
   }
 
@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(SIM_THREADS) k_sim(const __grid_constant__ Sim
   }
   TZ_STAMP(6);
   TZ_TL_MAX(P.pad0, 2);
-  tl_max(P.tl_row, 2, lane);
+  if (mode & MODE_TIMELINE) tl_max(P.tl_row, 2, lane);
 #ifdef TZ_PROFILE
   if (b == 0 && lane == 0) g_prof[7] = levels;
   if (b < 4096 && lane == 0) {
@@ -663,6 +663,11 @@ int launch_sim_k(K kernel, const SimLaunch& L, cudaStream_t s) {
 
 template <int NC, bool WEIGHTED, int SEL, int FM>
 int launch_sim_p(const SimLaunch& L, cudaStream_t s) {
+  if (L.P.cfg.q_transform == TZ_QT_IDENTITY) {  // (the other q_transforms are instantiated for ordinary launches only)
+    SimLaunch L2 = L;
+    L2.P.cfg.programmatic = 0;
+    return launch_sim_k(k_sim<NC, WEIGHTED, SEL | SELQ_IDENTITY, FM, false>, L2, s);
+  }
   if (use_pdl(L)) return launch_sim_k(k_sim<NC, WEIGHTED, SEL, FM, true>, L, s);
   return launch_sim_k(k_sim<NC, WEIGHTED, SEL, FM, false>, L, s);
 }

@@ -571,8 +571,8 @@ int launch_wide_any(const SimLaunch& L, int nc, int W, cudaStream_t s) {
   const bool mz = L.P.cfg.selector == TZ_SEL_MUZERO_PUCT;
 #define TZ_WIDE(NC_)                                                                  \
   do {                                                                                \
-    if (mz) return launch_wide_w<NC_, WEIGHTED, TZ_SEL_MUZERO_PUCT>(L, W, s);         \
-    return launch_wide_w<NC_, WEIGHTED, TZ_SEL_PUCT>(L, W, s);                        \
+    if (mz) return launch_wide_w<NC_, WEIGHTED, TZ_SEL_MUZERO_PUCT | SELQ_RUNTIME>(L, W, s); \
+    return launch_wide_w<NC_, WEIGHTED, TZ_SEL_PUCT | SELQ_RUNTIME>(L, W, s);         \
   } while (0)
   if (nc <= 1) TZ_WIDE(1);
   if (nc <= 2) TZ_WIDE(2);
