@@ -7,21 +7,9 @@
 
 namespace {
 
-// A node the walk passes that was not on the previous path will be a path node of the NEXT launch, whose second round trip
-// reads its statistics and its child_stats row: ask L2 for them now (fire-and-forget, one line per lane), so that the launch
-// after the user's leaf kernels finds them there instead of in DRAM (the step's L2 hit rate is ~40 %, profiles/r2a).
-__device__ __forceinline__ void walk_prefetch(const TV& tv, int cur, int F, int lane) {
-#ifndef TZ_NO_WALK_PREFETCH
-  const int lines = (16 * F + 127) >> 7;  // child_stats row, 128-byte lines (+1 for an unaligned start)
-  if (lane <= lines + 2) {
-    const char* a = lane == 0 ? reinterpret_cast<const char*>(tv.q + cur)
-                    : lane == 1 ? reinterpret_cast<const char*>(tv.n + cur)
-                                : reinterpret_cast<const char*>(tv.cs + (unsigned)cur * (unsigned)F) + 128 * (lane - 2);
-    prefetch_l2(a);
-  }
-#endif
-}
-
+// (Prefetching, during the walk, the rows the NEXT launch will read -- prefetch.global.L2 of q / n / the child_stats row of
+// every node the walk passes -- was measured 14 % SLOWER on configs[1] (profiles/r2m_variants.log): the walk is the kernel's
+// critical path and the prefetches queue ahead of its own loads.)
 // FM = 4 / 8 / 16: narrow plain-MCTS trees (F <= FM), decisions scored one lane per path level (narrow_select);
 // FM = 0: one lane per child with NC register chunks per lane, U levels side by side (any F, and the weighted
 // variant, whose levels are sequential).
@@ -532,7 +520,6 @@ __global__ void __launch_bounds__(SIM_THREADS) k_sim(const __grid_constant__ Sim
       by = new_by;
     } else {
       const int2 e = sb_live ? sb[cur] : tv.best[cur];  // the one dependent load of this level
-      walk_prefetch(tv, cur, F, lane);
       bx = e.x;
       by = e.y;
       if (bx < 0) {  // unknown: score the node here (PUCTSelector.__call__) and remember the decision
@@ -571,8 +558,7 @@ __global__ void __launch_bounds__(SIM_THREADS) k_sim(const __grid_constant__ Sim
         by = new_by;
       } else {
         const int2 e = sb_live ? sb[cur] : tv.best[cur];
-        walk_prefetch(tv, cur, F, lane);
-        bx = e.x;
+          bx = e.x;
         by = e.y;
         if (bx < 0) {
           Row<NC> row;

@@ -25,6 +25,7 @@ std::atomic<unsigned long long*> g_tl_rows{nullptr};
 std::atomic<uint32_t> g_tl_slots{0};
 std::atomic<uint64_t> g_leaf_seq{0};
 __device__ __forceinline__ unsigned long long gtime_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__constant__ unsigned long long* c_tl_rows;
 
 #ifdef TZ_PROFILE  // diagnostic build (libtz_synth_prof.so): per-launch timeline of k_leaf, see scripts/timeline.py
 __device__ unsigned long long g_tl[4 * 1024];  // {first warp in, last warp past griddepcontrol.wait, last warp out, -}
@@ -126,9 +127,12 @@ __global__ void __launch_bounds__(THREADS) k_root(const TzSynthGame g, const int
 __global__ void __launch_bounds__(THREADS) k_leaf(const TzSynthGame g, const int B, const int32_t* __restrict__ parent_core,
                                                 const int32_t* __restrict__ action, float* __restrict__ policy,
                                                 float* __restrict__ value, uint8_t* __restrict__ terminated, int32_t* new_core,
-                                                uint8_t* new_payload, const int pdl_and_slot, unsigned long long* tl_row) {
+                                                uint8_t* new_payload, const int pdl_and_slot) {
   const int pdl = pdl_and_slot & 1;
-  [[maybe_unused]] const int tl_slot = pdl_and_slot >> 1;  // diagnostic build: timeline slot of this launch
+  // optional launch record (tz_synth_set_timeline): bit 1 = on, the row index above it; the rows live behind a __constant__
+  // pointer so that the kernel's parameter list is the same with and without the record
+  unsigned long long* const tl_row = (pdl_and_slot & 2) ? c_tl_rows + 4 * (size_t)(pdl_and_slot >> 2) : nullptr;
+  [[maybe_unused]] const int tl_slot = pdl_and_slot >> 2;  // diagnostic build: timeline slot of this launch
   const int b = (int)((blockIdx.x * (unsigned)THREADS + threadIdx.x) >> 5), lane = threadIdx.x & 31;
   if (b >= B) return;
   TZ_TL(atomicMin, tl_slot, 0);
@@ -228,8 +232,11 @@ int tz_synth_debug_timeline(unsigned long long* out, int reset) {  // diagnostic
 
 int tz_synth_set_timeline(uint64_t* rows_dev, int slots) {
   if (rows_dev && (slots <= 0 || (slots & (slots - 1)) != 0)) return TZ_EINVAL;
+  unsigned long long* rows = reinterpret_cast<unsigned long long*>(rows_dev);
+  const cudaError_t e = cudaMemcpyToSymbol(c_tl_rows, &rows, sizeof(rows));
+  if (e != cudaSuccess) return (int)e;
   g_tl_slots.store(rows_dev ? (uint32_t)slots : 0u, std::memory_order_relaxed);
-  g_tl_rows.store(reinterpret_cast<unsigned long long*>(rows_dev), std::memory_order_relaxed);
+  g_tl_rows.store(rows, std::memory_order_relaxed);
   return TZ_OK;
 }
 
@@ -263,12 +270,12 @@ int tz_synth_leaf(const TzSynthGame* g, int B, const int32_t* parent_core, const
   if (!parent_core || !action || !policy || !value || !terminated || !new_core) return TZ_EINVAL;
   if (g->payload_bytes > 0 && !new_payload) return TZ_EINVAL;
 #ifdef TZ_PROFILE
-  const int tl_slot = (int)((g_tl_seq.fetch_add(1, std::memory_order_relaxed) & 1023u) << 1);
+  int tl_slot = (int)((g_tl_seq.fetch_add(1, std::memory_order_relaxed) & 1023u) << 2);
 #else
-  const int tl_slot = 0;
+  int tl_slot = 0;
+  if (g_tl_rows.load(std::memory_order_relaxed))
+    tl_slot = 2 | (int)((g_leaf_seq.fetch_add(1, std::memory_order_relaxed) & (uint64_t)(g_tl_slots.load(std::memory_order_relaxed) - 1)) << 2);
 #endif
-  unsigned long long* tl_row = g_tl_rows.load(std::memory_order_relaxed);
-  if (tl_row) tl_row += 4 * (g_leaf_seq.fetch_add(1, std::memory_order_relaxed) & (uint64_t)(g_tl_slots.load(std::memory_order_relaxed) - 1));
   if (g_programmatic.load(std::memory_order_relaxed)) {
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3((unsigned)grid_for(B));
@@ -279,12 +286,12 @@ int tz_synth_leaf(const TzSynthGame* g, int B, const int32_t* parent_core, const
     at[0].val.programmaticStreamSerializationAllowed = 1;
     lc.attrs = at;
     lc.numAttrs = 1;
-    const cudaError_t e = cudaLaunchKernelEx(&lc, k_leaf, *g, B, parent_core, action, policy, value, terminated, new_core, new_payload, 1 | tl_slot, tl_row);
+    const cudaError_t e = cudaLaunchKernelEx(&lc, k_leaf, *g, B, parent_core, action, policy, value, terminated, new_core, new_payload, 1 | tl_slot);
     g_launches.fetch_add(1, std::memory_order_relaxed);
     return e == cudaSuccess ? TZ_OK : (int)e;
   }
   k_leaf<<<grid_for(B), THREADS, 0, (cudaStream_t)stream>>>(*g, B, parent_core, action, policy, value, terminated, new_core,
-                                                          new_payload, 0 | tl_slot, tl_row);
+                                                          new_payload, 0 | tl_slot);
   return status();
 }
 
