@@ -397,9 +397,10 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         if sampler is not None:
             # the timed region may be shorter than a few sampling periods: keep the SAME load running (untimed replays of the
             # same step) until ~0.6 s of it has been sampled, so that the clocks line describes the GPU under this load
+            # (rank 0 only: the graph replay alone, never the step's collectives -- the other ranks are not in this loop)
             t_end = time.perf_counter() + max(0.0, 0.6 - ms_wall)
             while time.perf_counter() < t_end:
-                step()
+                replay()
                 torch.cuda.synchronize()
         clocks_ = sampler.stop() if sampler else None
         per_step = [a_.elapsed_time(b_) for a_, b_ in evs]
@@ -637,7 +638,9 @@ def run_native(args, out):
     torch.cuda.set_device(cx.local)
     cx.dev = torch.device("cuda", cx.local)
     if cx.world > 1:
-        dist.init_process_group("nccl", device_id=cx.dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=cx.dev, timeout=datetime.timedelta(seconds=180))
     cx.lib, cx.slib = _abi.lib(), _abi.synth_lib()
     cx.flush_buf = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=cx.dev)
     world, rank = cx.world, cx.rank

@@ -1,0 +1,8 @@
+#!/bin/bash
+TAG=${1:-r2n2b}
+O=gpurun_out
+mkdir -p $O
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus 2 --steps 6 --warmup 3 --named cfg5 --skip-cpu > $O/${TAG}_bench_forced.json 2> $O/${TAG}_bench_forced.err
+tail -3 $O/${TAG}_bench_forced.err | cut -c1-300; python -c "
+import json; d=json.load(open('$O/${TAG}_bench_forced.json')); print('N=2 forced:', d['value']/1e6, 'M sims/s', d['clocks'])
+for n in d['config']['named']: print(' named', n['name'], n['config']['envs_per_gpu'], 'envs/gpu', n['value']/1e6, 'M sims/s', n['ms_per_step'], 'ms e2e', n['e2e']['value']/1e6, n['config'].get('nccl'), n['config']['step'][-120:])"
