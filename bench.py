@@ -303,6 +303,42 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
 
     dn_d, rn_d, u_d = (torch.from_numpy(x).to(dev) for x in (dn_h, rn_h, u_h))
 
+    def make_replay(get_core, get_pw, get_done):
+        """configs[4] names "full self-play + replay memory": the collection step's buffer update (Trainer.collect,
+        core/training/train.py:300-340 -> tz_replay_collect) runs inside the step, fed from static buffers; with more than one
+        rank also the training step's two exchange steps, once per move, OUTSIDE the search (north star: "NCCL only for the
+        existing gradient mean and replay-memory gather"): one sample of TRAIN_BATCH rows over the buffers of all ranks
+        (replay_memory.py:137-183 / train.py:435-437: all-reduce of the valid count, all-gather of every rank's candidates,
+        all-reduce of the owners' rows) and the gradient mean (train.py:393,397) of a parameter-sized buffer, enqueued eagerly
+        after the graph replay.  Returns (collect(move_fn), after_step or None, extra config)."""
+        rb = tz.EpisodeReplayBuffer(capacity=REPLAY_CAPACITY)
+        obs0 = get_core().to(torch.float32)
+        rstate = rb.init(B, tz.BaseExperience(reward=torch.zeros((1,)), policy_weights=torch.zeros((F,)),
+                                              policy_mask=torch.zeros((F,), dtype=torch.bool), observation_nn=obs0[0].cpu(),
+                                              cur_player_id=torch.zeros((), dtype=torch.int32)), device=dev)
+        x_obs, x_mask = torch.empty_like(obs0), torch.ones((B, F), dtype=torch.bool, device=dev)
+        x_rew0, x_rew = torch.zeros((B, 1), device=dev), torch.empty((B, 1), device=dev)
+        x_player = torch.zeros((B,), dtype=torch.int32, device=dev)
+        x_trunc = torch.zeros((B,), dtype=torch.uint8, device=dev)
+
+        def collect(move_fn):
+            x_obs.copy_(get_core())  # the position the search runs on (int32 -> float32 features)
+            move_fn()
+            x_rew.copy_(get_done().unsqueeze(1))  # stand-in reward: 1 where the episode ended
+            exp = tz.BaseExperience(reward=x_rew0, policy_weights=get_pw(), policy_mask=x_mask, observation_nn=x_obs,
+                                    cur_player_id=x_player)
+            rb.collect_update(rstate, [exp], x_rew, get_done(), x_trunc)
+
+        if not with_nccl:
+            return collect, None, {}
+        grads = torch.zeros((GRAD_FLOATS,), dtype=torch.float32, device=dev)
+
+        def after():
+            rb.sample(rstate, 17, TRAIN_BATCH)
+            dist.all_reduce(grads, op=dist.ReduceOp.AVG)
+
+        return collect, after, {"nccl": {"replay_sample_rows": TRAIN_BATCH, "grad_allreduce_bytes": GRAD_FLOATS * 4}}
+
     # ---------------- leg 1: device-resident inputs, whole move in the C-ABI (tz_search + leaf callback) ----------
     def timed_moves(programmatic, with_clocks, keep):
         """W warm-up + K timed self-play moves (one CUDA-graph replay each, per-step events, L2 flushed in between)."""
@@ -319,38 +355,10 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         after_step = None
         extra = {}
         if with_replay:
-            # configs[4] names "full self-play + replay memory": the collection step's buffer update (Trainer.collect,
-            # core/training/train.py:300-340 -> tz_replay_collect) runs inside the step, fed from static buffers
-            rb = tz.EpisodeReplayBuffer(capacity=REPLAY_CAPACITY)
-            obs0 = sp_.state["core"].to(torch.float32)
-            rstate = rb.init(B, tz.BaseExperience(reward=torch.zeros((1,)), policy_weights=torch.zeros((F,)),
-                                                  policy_mask=torch.zeros((F,), dtype=torch.bool), observation_nn=obs0[0].cpu(),
-                                                  cur_player_id=torch.zeros((), dtype=torch.int32)), device=dev)
-            x_obs, x_mask = torch.empty_like(obs0), torch.ones((B, F), dtype=torch.bool, device=dev)
-            x_rew0, x_rew = torch.zeros((B, 1), device=dev), torch.empty((B, 1), device=dev)
-            x_player = torch.zeros((B,), dtype=torch.int32, device=dev)
-            x_trunc = torch.zeros((B,), dtype=torch.uint8, device=dev)
+            collect, after_step, extra = make_replay(lambda: sp_.state["core"], lambda: sp_.policy_weights, lambda: sp_.reset_flag)
 
             def one_move():
-                x_obs.copy_(sp_.state["core"])  # the position the search runs on (int32 -> float32 features)
-                sp_.move()
-                x_rew.copy_(sp_.reset_flag.unsqueeze(1))  # stand-in reward: 1 where the episode ended
-                exp = tz.BaseExperience(reward=x_rew0, policy_weights=sp_.policy_weights, policy_mask=x_mask,
-                                        observation_nn=x_obs, cur_player_id=x_player)
-                rb.collect_update(rstate, [exp], x_rew, sp_.reset_flag, x_trunc)
-
-            if with_nccl:
-                # the training step's two exchange steps, once per move, OUTSIDE the search (north star: "NCCL only for the
-                # existing gradient mean and replay-memory gather"): one sample of TRAIN_BATCH rows over the buffers of all
-                # ranks (replay_memory.py:137-183 / train.py:435-437: all-reduce of the valid count, all-gather of every
-                # rank's candidates, all-reduce of the owners' rows) and the gradient mean (train.py:393,397) of a
-                # parameter-sized buffer.  Enqueued eagerly after the graph replay.
-                grads = torch.zeros((GRAD_FLOATS,), dtype=torch.float32, device=dev)
-                extra["nccl"] = {"replay_sample_rows": TRAIN_BATCH, "grad_allreduce_bytes": GRAD_FLOATS * 4}
-
-                def after_step():
-                    rb.sample(rstate, 17, TRAIN_BATCH)
-                    dist.all_reduce(grads, op=dist.ReduceOp.AVG)
+                collect(sp_.move)
 
         l0 = launches()
         one_move()  # un-captured first move: loads modules, sizes caches
@@ -538,12 +546,27 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         s_dn, s_rn, s_u = s_in[:B * F].view(B, F), s_in[B * F:2 * B * F].view(B, F), s_in[2 * B * F:]
         out_box = {}
 
-        def user_step():
+        def api_move():
             out, _, _, _, _, _ = step_env_and_evaluator(
                 key=None, env_state=env.state, env_state_metadata=env.metadata(), eval_state=tree2, params=None,
                 evaluator=ev2, env_step_fn=env.env_step_fn, env_init_fn=None, max_steps=1 << 30,
                 leaf_fn=game.leaf_fn, root_noise=s_rn, uniform01=s_u, dirichlet_noise=s_dn)
             out_box["action"], out_box["pw"] = out.action, out.policy_weights
+
+        user_step, e2e_after = api_move, None
+        if with_replay:  # the same step as `value`: replay-buffer update inside, the NCCL legs behind it
+            out_box["pw"] = torch.zeros((B, F), dtype=torch.float32, device=dev)
+            pw_static = out_box["pw"]
+
+            def api_move_static():
+                api_move()
+                pw_static.copy_(out_box["pw"])
+                out_box["pw"] = pw_static
+
+            collect2, e2e_after, _ = make_replay(lambda: env.state["core"], lambda: pw_static, lambda: env.reset_flag)
+
+            def user_step():
+                collect2(api_move_static)
 
         in_p = torch.from_numpy(np.concatenate([dn_h.reshape(total, -1), rn_h.reshape(total, -1), u_h.reshape(total, -1)],
                                                axis=1)).pin_memory()  # [steps, 2BF + B], pinned
@@ -573,6 +596,8 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         def e2e_step(i):
             h2d(i)
             api_step()
+            if e2e_after:
+                e2e_after()
             act_p.copy_(out_box["action"], non_blocking=True)
             pw_p.copy_(out_box["pw"], non_blocking=True)
             torch.cuda.synchronize()  # the host needs the actions before it can go on
