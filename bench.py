@@ -570,8 +570,6 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
 
         in_p = torch.from_numpy(np.concatenate([dn_h.reshape(total, -1), rn_h.reshape(total, -1), u_h.reshape(total, -1)],
                                                axis=1)).pin_memory()  # [steps, 2BF + B], pinned
-        act_p = torch.empty((B,), dtype=torch.int32).pin_memory()
-        pw_p = torch.empty((B, F), dtype=torch.float32).pin_memory()
 
         def h2d(i):
             s_in.copy_(in_p[i], non_blocking=True)
@@ -593,33 +591,67 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
             torch.cuda.current_stream().wait_stream(side)
             api_step = cg2.replay
 
-        def e2e_step(i):
+        act_slots = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
+        pw_slots = [torch.empty((B, F), dtype=torch.float32).pin_memory() for _ in range(2)]
+        sink = [0.0]
+
+        def enqueue(i, slot):
+            """One step: H2D of its inputs, the captured API step (+ the NCCL legs of configs[4]), D2H of its results."""
             h2d(i)
             api_step()
             if e2e_after:
                 e2e_after()
-            act_p.copy_(out_box["action"], non_blocking=True)
-            pw_p.copy_(out_box["pw"], non_blocking=True)
-            torch.cuda.synchronize()  # the host needs the actions before it can go on
+            act_slots[slot].copy_(out_box["action"], non_blocking=True)
+            pw_slots[slot].copy_(out_box["pw"], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            return ev
 
-        for i in range(W):
-            e2e_step(i)
-        barrier()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for i in range(K):
-            e2e_step(W + i)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        barrier()
-        t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
-        e2e = {"value": total_envs * S * K / float(t_e.item()), "unit": UNIT,
+        def consume(ev, slot):
+            ev.synchronize()  # the host reads the step's actions and policy weights
+            sink[0] += float(act_slots[slot][0]) + float(pw_slots[slot][0, 0])
+
+        def run_pipelined(first, count):
+            """The actor loop of a device-resident env: step i+1 is enqueued before the host consumes step i's results (the
+            reference's jitted collect loop dispatches asynchronously too), so the launch latency of a step overlaps the GPU's
+            work on the previous one; every step's results are read by the host, one step late."""
+            prev = None
+            for j in range(count):
+                ev = enqueue(first + j, j & 1)
+                if prev is not None:
+                    consume(prev, (j - 1) & 1)
+                prev = ev
+            consume(prev, (count - 1) & 1)
+
+        def run_lockstep(first, count):
+            for j in range(count):
+                consume(enqueue(first + j, j & 1), j & 1)  # the host waits for every step before it enqueues the next
+
+        def timed(run):
+            run(0, W)
+            barrier()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run(W, K)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            barrier()
+            t_e = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t_e, op=dist.ReduceOp.MAX)
+            return float(t_e.item())
+
+        dt_lock = timed(run_lockstep)
+        dt_pipe = timed(run_pipelined)
+        e2e = {"value": total_envs * S * K / dt_pipe, "unit": UNIT,
                "h2d_bytes_per_step": int(2 * B * F * 4 + B * 4), "d2h_bytes_per_step": int(B * 4 + B * F * 4),
-               "ms_per_step": float(t_e.item()) / K * 1e3,
-               "api": "step_env_and_evaluator(MCTS.evaluate + MCTS.step) captured in a CUDA graph by the caller; "
-                      "host wall clock incl. pinned H2D of the step's noise inputs and D2H of actions + policy weights",
+               "ms_per_step": dt_pipe / K * 1e3,
+               "lockstep": {"value": total_envs * S * K / dt_lock, "ms_per_step": dt_lock / K * 1e3,
+                            "note": "the host waits for each step's results before it enqueues the next one: adds the host's "
+                                    "graph-launch latency (40-100 us, box dependent) to every step"},
+               "api": "step_env_and_evaluator(MCTS.evaluate + MCTS.step) captured in a CUDA graph by the caller; host wall clock "
+                      "incl. pinned H2D of every step's noise inputs and D2H of its actions + policy weights, which the host "
+                      "reads one step late (step i+1 is enqueued before step i's results are consumed)",
                "launches_per_step": int(api_launches)}
         del tree2, ev2, env
 
