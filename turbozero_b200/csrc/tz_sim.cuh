@@ -10,7 +10,7 @@ namespace {
 // (Prefetching, during the walk, the rows the NEXT launch will read -- prefetch.global.L2 of q / n / the child_stats row of
 // every node the walk passes -- was measured 14 % SLOWER on configs[1] (profiles/r2m_variants.log): the walk is the kernel's
 // critical path and the prefetches queue ahead of its own loads.)
-// FM = 4 / 8 / 16: narrow plain-MCTS trees (F <= FM), decisions scored four lanes per path level (quad_select);
+// FM = 4 / 8 / 16: narrow plain-MCTS trees (F <= FM), decisions scored one lane per path level (narrow_select);
 // FM = 0: one lane per child with NC register chunks per lane, U levels side by side (any F, and the weighted
 // variant, whose levels are sequential).
 template <int NC, bool WEIGHTED, int SEL, int FM, bool PDL>
@@ -162,23 +162,12 @@ __global__ void __launch_bounds__(SIM_THREADS) k_sim(const __grid_constant__ Sim
         q_e = tv.q[end_child];
       }
       TZ_STAMP(10);
-      // narrow trees: FOUR lanes per path level (quad_select), eight levels per pass, up to four passes for the 32 ring levels.
-      // Quad g = lane >> 2 scores level top - (8 p + g) in pass p; lane j = lane & 3 of the quad holds children j, j + 4, ...
-      constexpr int CPL = NARROW ? FM / 4 : 1;   // children per lane
-      constexpr int QP = NARROW ? 4 : 1;         // passes
-      int4 hq[QP][CPL];
-      const int qg = lane >> 2, qj = lane & 3;
+      int4 h[NARROW ? FM : 1];  // narrow: this lane's path node's whole child_stats row
       Row<NC> rows[U];
       if constexpr (NARROW) {
+        const int4* hrow = tv.cs + (unsigned)(on_path ? pn : 0) * (unsigned)F;
 #pragma unroll
-        for (int pss = 0; pss < QP; ++pss) {
-          const int dl = top - (8 * pss + qg);  // the level this quad scores in pass pss
-          const bool vl = dl >= lowest;
-          const int nodel = __shfl_sync(FULL, pn, dl & 31);
-          const int4* hrow = tv.cs + (unsigned)(vl ? nodel : 0) * (unsigned)F;
-#pragma unroll
-          for (int c = 0; c < CPL; ++c) hq[pss][c] = (vl && qj + 4 * c < F) ? hrow[qj + 4 * c] : make_int4(0, 0, 0, -1);
-        }
+        for (int a = 0; a < FM; ++a) h[a] = (on_path && a < F) ? hrow[a] : make_int4(0, 0, 0, -1);
       } else {
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -265,54 +254,36 @@ __global__ void __launch_bounds__(SIM_THREADS) k_sim(const __grid_constant__ Sim
       // ---- every path node's selector decision with the statistics it will have when the next walk arrives
       //      (weighted: preceded by the node's backup, deepest level first) ----------------------------------------
       if constexpr (NARROW) {
-        const int my_pass = (top - d) >> 3, my_quad = (top - d) & 7;  // where this lane's own level is scored
+        // the child this path went through at this level, with its statistics as of now: from the lane one level down
+        const float pq_up = __shfl_sync(FULL, q1, (lane + 1) & 31);
+        const int pnb_up = __shfl_sync(FULL, n1, (lane + 1) & 31);
+        const bool is_top = d == top;
+        const float pq = is_top ? cq : pq_up;
+        const int pnb = is_top ? cnbits : pnb_up;
+        const bool patch = on_path && (!is_top || node >= 0);
 #pragma unroll
-        for (int pss = 0; pss < QP; ++pss) {
-          if (top - 8 * pss < lowest) continue;  // (uniform) no level left for this pass
-          const int dl = top - (8 * pss + qg);
-          const bool vl = dl >= lowest;
-          const int sl = dl & 31;
-          // the level's own new statistics, the action the path took there, and the child it went through with ITS statistics
-          // as of now (the expanded child at the top level, else the level one down): all held by the level's owner lanes
-          const float q1_l = __shfl_sync(FULL, q1, sl), sq_l = __shfl_sync(FULL, sq1, sl), sc_l = __shfl_sync(FULL, scale1, sl);
-          const int pa_l = __shfl_sync(FULL, pa, sl);
-          const float pq_up = __shfl_sync(FULL, q1, (sl + 1) & 31);
-          const int pnb_up = __shfl_sync(FULL, n1, (sl + 1) & 31);
-          const bool is_top = dl == top;
-          const float pq = is_top ? cq : pq_up;
-          const int pnb = is_top ? cnbits : pnb_up;
-          const bool patch = vl && (!is_top || node >= 0);
+        for (int a = 0; a < FM; ++a) {
+          if (patch && a == pa) {
+            h[a].x = __float_as_int(pq);
+            h[a].y = pnb;
+            if (is_top) h[a].w = node;
+          }
+        }
+        bool unsafe = false;
+        int act = narrow_select<FM, SEL, false>(h, F, cfg, q1, sq1, scale1, unsafe);
+        if (__any_sync(FULL, on_path && unsafe))  // rare: operands outside div_core's proven range -> hardware division
+          act = narrow_select<FM, SEL, true>(h, F, cfg, q1, sq1, scale1, unsafe);
+        int child = h[0].w, cnb = h[0].y;
 #pragma unroll
-          for (int c = 0; c < CPL; ++c) {
-            if (patch && qj + 4 * c == pa_l) {
-              hq[pss][c].x = __float_as_int(pq);
-              hq[pss][c].y = pnb;
-              if (is_top) hq[pss][c].w = node;
-            }
+        for (int a = 1; a < FM; ++a) {
+          if (a == act) {
+            child = h[a].w;
+            cnb = h[a].y;
           }
-          bool unsafe = false;
-          int act = quad_select<CPL, SEL, false>(hq[pss], F, qj, cfg, q1_l, sq_l, sc_l, unsafe);
-          if (__any_sync(FULL, vl && unsafe))  // rare: operands outside div_core's proven range -> hardware division
-            act = quad_select<CPL, SEL, true>(hq[pss], F, qj, cfg, q1_l, sq_l, sc_l, unsafe);
-          // the chosen child's edge and statistics sit in lane (act & 3) of the quad, entry act >> 2
-          int child = hq[pss][0].w, cnb = hq[pss][0].y;
-#pragma unroll
-          for (int c = 1; c < CPL; ++c) {
-            if (c == (act >> 2)) {
-              child = hq[pss][c].w;
-              cnb = hq[pss][c].y;
-            }
-          }
-          const int from = (lane & ~3) | (act & 3);
-          child = __shfl_sync(FULL, child, from);
-          cnb = __shfl_sync(FULL, cnb, from);
-          const int ey = child < 0 ? -1 : (cnb < 0 ? -(child + 2) : child);  // best-table entry (see TzTree.best)
-          // hand the entry to the lane that owns the level
-          const int got_x = __shfl_sync(FULL, act, 4 * my_quad), got_y = __shfl_sync(FULL, ey, 4 * my_quad);
-          if (on_path && my_pass == pss) {
-            my_bx = got_x;
-            my_by = got_y;
-          }
+        }
+        if (on_path) {  // best-table entry (see TzTree.best)
+          my_bx = act;
+          my_by = child < 0 ? -1 : (cnb < 0 ? -(child + 2) : child);
         }
       } else {
         float below_q = cq;  // weighted: statistics of the path child one level down, as of now
