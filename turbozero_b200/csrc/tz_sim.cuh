@@ -10,6 +10,10 @@ namespace {
 // (Prefetching, during the walk, the rows the NEXT launch will read -- prefetch.global.L2 of q / n / the child_stats row of
 // every node the walk passes -- was measured 14 % SLOWER on configs[1] (profiles/r2m_variants.log): the walk is the kernel's
 // critical path and the prefetches queue ahead of its own loads.)
+// (Four lanes per path level -- quads scoring eight levels per pass, min / max / argmax by two xor-shuffle steps -- was built
+// and measured in round 2: the median warp's decisions fell from 0.90 to 0.67 us, but a deep path needs up to four passes
+// (1.18 us for the slowest warps, which end the launch) and issuing the rows quad-wise cost 0.4 us more: 117.2 instead of
+// 119.4 M simulations/s on configs[1].  Reverted; profiles/r2p_variants.log, r2q_phase_warps.log.)
 // FM = 4 / 8 / 16: narrow plain-MCTS trees (F <= FM), decisions scored one lane per path level (narrow_select);
 // FM = 0: one lane per child with NC register chunks per lane, U levels side by side (any F, and the weighted
 // variant, whose levels are sequential).
