@@ -270,7 +270,7 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
 
     tz, _abi, lib, slib, dev, rank, world, args = cx.tz, cx._abi, cx.lib, cx.slib, cx.dev, cx.rank, cx.world, cx.args
     from turbozero_b200.common import step_env_and_evaluator
-    from turbozero_b200.synthetic import SyntheticEnv, SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
+    from standin.synthetic import SyntheticEnv, SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
 
     name, _, S, N, weighted, discount, desc = WORKLOADS[wl]
     seed = 1000 + rank
@@ -683,6 +683,7 @@ def run_native(args, out):
     import torch.distributed as dist
 
     import turbozero_b200 as tz
+    from standin import abi as _sabi
     from turbozero_b200 import _abi
 
     if not torch.cuda.is_available():
@@ -698,7 +699,7 @@ def run_native(args, out):
         import datetime
 
         dist.init_process_group("nccl", device_id=cx.dev, timeout=datetime.timedelta(seconds=180))
-    cx.lib, cx.slib = _abi.lib(), _abi.synth_lib()
+    cx.lib, cx.slib = _abi.lib(), _sabi.synth_lib()
     cx.flush_buf = None if args.no_flush else torch.empty(512 << 20, dtype=torch.uint8, device=cx.dev)
     world, rank = cx.world, cx.rank
 

@@ -18,14 +18,15 @@ FLAGS = ["-O2", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-fvisibility
 
 def build(force: bool = False) -> Path:
     OUT_DIR.mkdir(exist_ok=True)
-    srcs = [HERE / "tz_oracle.c", *sorted((ROOT / "include").glob("*.h"))]
+    srcs = [HERE / "tz_oracle.c", *sorted((ROOT / "include").glob("*.h")), *sorted((ROOT / "standin" / "include").glob("*.h"))]
     h = hashlib.sha256(" ".join(FLAGS).encode())
     for s in srcs:
         h.update(s.read_bytes())
     stamp = OUT_DIR / "libtz_oracle.sha256"
     if not force and OUT.exists() and stamp.exists() and stamp.read_text().strip() == h.hexdigest():
         return OUT
-    cmd = ["gcc", *FLAGS, f"-I{ROOT / 'include'}", str(HERE / "tz_oracle.c"), "-o", str(OUT), "-lm"]
+    # (standin/include/tz_synth.h: the synthetic game's inline definition, shared with the device stand-in)
+    cmd = ["gcc", *FLAGS, f"-I{ROOT / 'include'}", f"-I{ROOT / 'standin' / 'include'}", str(HERE / "tz_oracle.c"), "-o", str(OUT), "-lm"]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError(f"gcc failed:\n{res.stderr}")

@@ -9,7 +9,8 @@ from typing import List, Optional, Sequence
 
 import numpy as np
 
-from turbozero_b200._abi import TZ_MAX_EMB, TzSearchCfg, TzSynthGame, TzTree, TzWork  # struct layouts only
+from standin.abi import TzSynthGame  # struct layout only (standin/include/tz_synth.h)
+from turbozero_b200._abi import TZ_MAX_EMB, TzSearchCfg, TzTree, TzWork  # struct layouts only
 from . import build as _build
 
 _lib = None

@@ -1,4 +1,4 @@
-"""ORACLE (test infrastructure) -- NumPy restatement of the synthetic hash game (include/tz_synth.h) and a
+"""ORACLE (test infrastructure) -- NumPy restatement of the synthetic hash game (standin/include/tz_synth.h) and a
 per-tree self-play driver that wires it to oracle/mcts_numpy.py exactly the way the reference wires a pgx
 env + network into MCTS (core/evaluators/mcts/mcts.py:71-108,145-189; core/evaluators/alphazero.py:43-81;
 core/common.py:32-103).  Written independently of the C/CUDA definition so the two can pin each other.

@@ -462,7 +462,7 @@ EXPORT int tzo_reroot(const TzTree* t, const int32_t* action, const uint8_t* res
 }
 
 /* ------------------------------------------------------------------------------------------------ */
-/* synthetic game on the host (same inline definition as the device stand-in, include/tz_synth.h)     */
+/* synthetic game on the host (same inline definition as the device stand-in, standin/include/tz_synth.h)     */
 /* ------------------------------------------------------------------------------------------------ */
 static void synth_write_state(const TzSynthGame* g, uint32_t h, int depth, int player, int32_t* core, uint8_t* payload) {
   core[0] = (int32_t)h;

@@ -5,3 +5,4 @@
 set -e
 cd "$(dirname "$0")/.."
 python -m turbozero_b200.build --prof "$@"
+python -m standin.build --prof "$@"

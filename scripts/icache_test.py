@@ -6,10 +6,11 @@ import ctypes as C, os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from turbozero_b200 import _abi
+from standin import abi as _sabi
 _orig = _abi._load
 _abi._load = lambda name, symbols: _orig("libtz_b200_prof.so" if name == "libtz_b200.so" else name, symbols)
 import turbozero_b200 as tz
-from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
+from standin.synthetic import SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
 
 def make(name, B, S, N):
     game = SyntheticGame.named(name, 1234)
@@ -27,7 +28,7 @@ def run(order, name="connect_four", B=256, S=128, N=256):
         A.move(); Bp.move()
     torch.cuda.synchronize()
     st = torch.cuda.current_stream().cuda_stream
-    leaf = _abi.synth_lib().tz_synth_leaf_cb
+    leaf = _sabi.synth_lib().tz_synth_leaf_cb
     def begin(sp):
         ts = sp.tree.struct()
         sp.game.root_eval(sp.state, sp.dir_noise, sp.dir_eps, out=(sp.root_policy, sp.root_value))

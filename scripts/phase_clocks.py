@@ -3,12 +3,14 @@ import ctypes as C, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from turbozero_b200 import _abi
+from standin import abi as _sabi
 _orig = _abi._load
-def _load(name, symbols):
-    return _orig("libtz_b200_prof.so" if name == "libtz_b200.so" else name, symbols)
+def _load(name, symbols, lib_dir=None):
+    return _orig("libtz_b200_prof.so" if name == "libtz_b200.so" else name, symbols, lib_dir)
 _abi._load = _load
+_sabi._load = lambda name, symbols, lib_dir=None: _orig(name, symbols, lib_dir)
 import turbozero_b200 as tz
-from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
+from standin.synthetic import SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
 
 def run(name, B, S, N, weighted=False):
     game = SyntheticGame.named(name, 1234)
@@ -34,7 +36,7 @@ def run(name, B, S, N, weighted=False):
     spans, worst = [], []
     rows = []
     fn, user, _ = sp._cb
-    leaf = _abi.synth_lib().tz_synth_leaf_cb
+    leaf = _sabi.synth_lib().tz_synth_leaf_cb
     for s in range(S - 1):
         leaf(user, s, C.byref(sp.work), st)
         lib.tz_expand_backprop_select(C.byref(ts), C.byref(sp.cfg), C.byref(sp.work), st)

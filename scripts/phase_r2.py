@@ -4,12 +4,14 @@ import ctypes as C, os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from turbozero_b200 import _abi
+from standin import abi as _sabi
 _orig = _abi._load
-def _load(name, symbols):
-    return _orig("libtz_b200_prof.so" if name == "libtz_b200.so" else name, symbols)
+def _load(name, symbols, lib_dir=None):
+    return _orig("libtz_b200_prof.so" if name == "libtz_b200.so" else name, symbols, lib_dir)
 _abi._load = _load
+_sabi._load = lambda name, symbols, lib_dir=None: _orig(name, symbols, lib_dir)
 import turbozero_b200 as tz
-from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
+from standin.synthetic import SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
 
 
 def setup(name, B, S, N, warps, weighted):
@@ -53,7 +55,7 @@ def wide(name, B, S, N, warps, weighted):
     nw = min(B, 4096)
     gbuf = (C.c_longlong * (16 * nw))()
     fn, user, _ = sp._cb
-    leaf = _abi.synth_lib().tz_synth_leaf_cb
+    leaf = _sabi.synth_lib().tz_synth_leaf_cb
     names = ["entry -> record checked (RT1)", "RT2 + backup", "decisions (+ expansion writes)", "vote", "walk", "embedding rows"]
     acc = []
     for s in range(S - 1):

@@ -3,7 +3,7 @@ import sys, time, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import turbozero_b200 as tz
-from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay
+from standin.synthetic import SyntheticGame, SyntheticSelfPlay
 
 def run(name, B, S, N, weighted=False, moves=8, warm=3, graph=True, use_path=True, pipelines=1, pdl=True):
     game = SyntheticGame.named(name, 1234)
@@ -11,8 +11,8 @@ def run(name, B, S, N, weighted=False, moves=8, warm=3, graph=True, use_path=Tru
     kw = dict(eval_fn=None, action_selector=tz.PUCTSelector(), branching_factor=game.F, max_nodes=N, num_iterations=S)
     ev = base(**kw)
     ev.programmatic_launch = pdl
-    from turbozero_b200 import _abi
-    _abi.synth_lib().tz_synth_set_programmatic(1 if pdl else 0)
+    from standin import abi as _sabi
+    _sabi.synth_lib().tz_synth_set_programmatic(1 if pdl else 0)
     sp = SyntheticSelfPlay(game, ev, B, dirichlet=True, use_path=use_path, pipelines=pipelines)
     sp.dir_noise.copy_(torch.distributions.Dirichlet(torch.full((B, game.F), 0.3)).sample().cuda())
     sp.uniform01.uniform_()

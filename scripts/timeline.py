@@ -5,12 +5,14 @@ import ctypes as C, os, statistics, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from turbozero_b200 import _abi
+from standin import abi as _sabi
 _orig = _abi._load
-def _load(name, symbols):
-    return _orig({"libtz_b200.so": "libtz_b200_prof.so", "libtz_synth.so": "libtz_synth_prof.so"}.get(name, name), symbols)
+def _load(name, symbols, lib_dir=None):
+    return _orig({"libtz_b200.so": "libtz_b200_prof.so", "libtz_synth.so": "libtz_synth_prof.so"}.get(name, name), symbols, lib_dir)
 _abi._load = _load
+_sabi._load = _load
 import turbozero_b200 as tz
-from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
+from standin.synthetic import SyntheticGame, SyntheticSelfPlay, make_synthetic_evaluator
 
 
 def read(fn, reset):
@@ -25,7 +27,7 @@ def run(name, B, S, N, programmatic):
     game = SyntheticGame.named(name, 1234)
     ev = make_synthetic_evaluator(tz.MCTS, game, action_selector=tz.PUCTSelector(), max_nodes=N, num_iterations=S,
                                   programmatic=programmatic)
-    _abi.synth_lib().tz_synth_set_programmatic(1 if programmatic else 0)
+    _sabi.synth_lib().tz_synth_set_programmatic(1 if programmatic else 0)
     sp = SyntheticSelfPlay(game, ev, B)
     sp.dir_noise.copy_(torch.distributions.Dirichlet(torch.full((B, game.F), 0.3)).sample().cuda())
     sp.uniform01.uniform_()
@@ -38,7 +40,7 @@ def run(name, B, S, N, programmatic):
     torch.cuda.current_stream().wait_stream(side)
     for _ in range(4): cg.replay()
     torch.cuda.synchronize()
-    lib, slib = _abi.lib(), _abi.synth_lib()
+    lib, slib = _abi.lib(), _sabi.synth_lib()
     read(lib.tz_debug_timeline, 1); read(slib.tz_synth_debug_timeline, 1)
     cg.replay(); torch.cuda.synchronize()
     sims, leaves = read(lib.tz_debug_timeline, 0), read(slib.tz_synth_debug_timeline, 0)

@@ -1,4 +1,4 @@
-// tz_synth.cu -- device-side synthetic game + "network" (include/tz_synth.h): the stand-in for the user's pgx
+// tz_synth.cu -- device-side synthetic game + "network" (standin/include/tz_synth.h): the stand-in for the user's pgx
 // env_step_fn / env_init_fn and eval_fn (core/types.py:27-31) plus MCTS.iterate's host glue (mcts.py:165-172)
 // and the root evaluation (mcts.py:137-138, alphazero.py:57-76).  Bench / test infrastructure only -- it is a
 // separate library (libtz_synth.so) and nothing in libtz_b200.so depends on it.

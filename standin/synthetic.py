@@ -1,4 +1,4 @@
-"""Device-side synthetic game (libtz_synth.so, include/tz_synth.h) wrapped for PyTorch.
+"""Device-side synthetic game (libtz_synth.so, standin/include/tz_synth.h) wrapped for PyTorch.
 
 Stand-in for the user's pgx environment + network, which cannot run in this image.  Used by bench.py, the GPU
 parity tests and smoke(); it is not part of the product path (the search never depends on it).
@@ -11,8 +11,10 @@ from typing import Dict, Optional, Tuple
 
 import torch
 
-from . import _abi
-from .trees import Tree, _stream_ptr
+from turbozero_b200 import _abi
+from turbozero_b200.trees import Tree, _stream_ptr
+
+from . import abi as _sabi
 
 # name: (F, payload_bytes, rho256, tau1024, max_depth): shapes of BASELINE.json's pgx games
 GAMES = {
@@ -39,7 +41,7 @@ class SyntheticGame:
         return cls(F, P, rho, tau, D, seed)
 
     def __post_init__(self):
-        self._c = _abi.TzSynthGame(F=self.F, payload_bytes=self.payload_bytes, rho256=self.rho256, tau1024=self.tau1024,
+        self._c = _sabi.TzSynthGame(F=self.F, payload_bytes=self.payload_bytes, rho256=self.rho256, tau1024=self.tau1024,
                                    max_depth=self.max_depth, seed=self.seed)
         self._out: Dict[int, tuple] = {}
 
@@ -59,7 +61,7 @@ class SyntheticGame:
         state = {"core": torch.empty((B, 4), dtype=torch.int32, device=device)}
         if self.payload_bytes > 0:
             state["payload"] = torch.empty((B, self.payload_bytes), dtype=torch.uint8, device=device)
-        _abi.check(_abi.synth_lib().tz_synth_init_states(C.byref(self._c), B, env_offset, episode.data_ptr(),
+        _abi.check(_sabi.synth_lib().tz_synth_init_states(C.byref(self._c), B, env_offset, episode.data_ptr(),
                                                          state["core"].data_ptr(), self._pay(state), _stream_ptr()),
                    "tz_synth_init_states")
         return state, episode
@@ -74,7 +76,7 @@ class SyntheticGame:
         B, dev = state["core"].shape[0], state["core"].device
         pol, val = out if out is not None else (torch.empty((B, self.F), dtype=torch.float32, device=dev),
                                                 torch.empty((B,), dtype=torch.float32, device=dev))
-        _abi.check(_abi.synth_lib().tz_synth_root(C.byref(self._c), B, state["core"].data_ptr(),
+        _abi.check(_sabi.synth_lib().tz_synth_root(C.byref(self._c), B, state["core"].data_ptr(),
                                                   None if dir_noise is None else dir_noise.data_ptr(), dir_eps,
                                                   pol.data_ptr(), val.data_ptr(), _stream_ptr()), "tz_synth_root")
         return pol, val
@@ -91,7 +93,7 @@ class SyntheticGame:
                     torch.empty((B,), dtype=torch.float32, device=dev), torch.empty((B,), dtype=torch.uint8, device=dev))
             self._out[B] = bufs
         new, pol, val, term = bufs
-        _abi.check(_abi.synth_lib().tz_synth_leaf(C.byref(self._c), B, parent_emb["core"].data_ptr(), action.data_ptr(),
+        _abi.check(_sabi.synth_lib().tz_synth_leaf(C.byref(self._c), B, parent_emb["core"].data_ptr(), action.data_ptr(),
                                                   pol.data_ptr(), val.data_ptr(), term.data_ptr(), new["core"].data_ptr(),
                                                   self._pay(new), _stream_ptr()), "tz_synth_leaf")
         return new, pol, val, term
@@ -99,15 +101,15 @@ class SyntheticGame:
     # --- real environment step after a move (common.py:82-99) ---
     def env_step(self, state, action: torch.Tensor, episode: torch.Tensor, reset_flag: torch.Tensor, env_offset: int = 0):
         B = action.shape[0]
-        _abi.check(_abi.synth_lib().tz_synth_env_step(C.byref(self._c), B, env_offset, action.data_ptr(),
+        _abi.check(_sabi.synth_lib().tz_synth_env_step(C.byref(self._c), B, env_offset, action.data_ptr(),
                                                       state["core"].data_ptr(), self._pay(state), episode.data_ptr(),
                                                       reset_flag.data_ptr(), _stream_ptr()), "tz_synth_env_step")
         return state
 
     def leaf_callback(self, B: int):
         """(function pointer, user pointer, keepalive) for tz_search: the whole simulation loop stays in C."""
-        ctx = _abi.TzSynthCtx(game=self._c, B=B)
-        fn = C.cast(_abi.synth_lib().tz_synth_leaf_cb, C.c_void_p)
+        ctx = _sabi.TzSynthCtx(game=self._c, B=B)
+        fn = C.cast(_sabi.synth_lib().tz_synth_leaf_cb, C.c_void_p)
         return fn, C.cast(C.pointer(ctx), C.c_void_p), ctx
 
 
@@ -229,11 +231,11 @@ class SyntheticSelfPlay:
         self._tl_search, self._tl_leaf = init.clone(), init.clone()
         self.lanes[0].work.timeline = self._tl_search.data_ptr()
         self.lanes[0].work.timeline_slots = self.TL_SLOTS
-        _abi.check(_abi.synth_lib().tz_synth_set_timeline(self._tl_leaf.data_ptr(), self.TL_SLOTS), "tz_synth_set_timeline")
+        _abi.check(_sabi.synth_lib().tz_synth_set_timeline(self._tl_leaf.data_ptr(), self.TL_SLOTS), "tz_synth_set_timeline")
 
     def timeline_mark(self):
         """(search seq, leaf seq) of the next launches: call right before issuing / capturing the move to be read."""
-        return int(_abi.lib().tz_launch_seq()), int(_abi.synth_lib().tz_synth_leaf_seq())
+        return int(_abi.lib().tz_launch_seq()), int(_sabi.synth_lib().tz_synth_leaf_seq())
 
     def timeline_clear(self) -> None:
         self._tl_search.copy_(self._tl_init)
@@ -249,7 +251,7 @@ class SyntheticSelfPlay:
     def timeline_end(self) -> None:
         self.lanes[0].work.timeline = None
         self.lanes[0].work.timeline_slots = 0
-        _abi.check(_abi.synth_lib().tz_synth_set_timeline(None, 0), "tz_synth_set_timeline")
+        _abi.check(_sabi.synth_lib().tz_synth_set_timeline(None, 0), "tz_synth_set_timeline")
 
     def launches_per_move(self) -> int:
         S = self.ev.num_iterations
@@ -289,7 +291,7 @@ def make_synthetic_evaluator(base, game: SyntheticGame, dir_eps: Optional[float]
     ev.fma_backup = fma_backup
     ev.programmatic_launch = programmatic
     if programmatic:  # the stand-in's leaf kernel then waits-then-signals, as TzSearchCfg.programmatic requires
-        _abi.synth_lib().tz_synth_set_programmatic(1)
+        _sabi.synth_lib().tz_synth_set_programmatic(1)
     ev.dirichlet_epsilon = dir_eps
     return ev
 

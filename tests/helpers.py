@@ -268,7 +268,7 @@ def assert_best_table_consistent(tree, ev, what="", expect_known=True):
 
 def make_cuda_evaluator(s: Schedule, game):
     import turbozero_b200 as tz
-    from turbozero_b200.synthetic import make_synthetic_evaluator
+    from standin.synthetic import make_synthetic_evaluator
 
     qt = {0: tz.normalize_q_values, 1: "identity"}[s.q_transform]
     sel = tz.PUCTSelector(c=s.c, q_transform=qt) if s.selector == 0 else tz.MuZeroPUCTSelector(c1=s.c1, c2=s.c2, q_transform=qt)
@@ -285,7 +285,7 @@ def make_cuda_evaluator(s: Schedule, game):
 def run_cuda_api(s: Schedule, fused: bool = True, snapshots: bool = False) -> Result:
     """The CUDA path through the Python mirror of the reference API (MCTS.evaluate / iterate / step)."""
     import torch
-    from turbozero_b200.synthetic import SyntheticGame
+    from standin.synthetic import SyntheticGame
 
     g = s.game
     game = SyntheticGame(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)
@@ -328,7 +328,7 @@ def run_cuda_api(s: Schedule, fused: bool = True, snapshots: bool = False) -> Re
 def run_cuda_selfplay(s: Schedule, use_path: bool = True, graph: bool = False, pipelines: int = 1, use_spill: bool = True) -> Result:
     """The CUDA path with the whole simulation loop inside the C-ABI (tz_search + tz_synth_leaf_cb)."""
     import torch
-    from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay
+    from standin.synthetic import SyntheticGame, SyntheticSelfPlay
 
     g = s.game
     game = SyntheticGame(g.F, g.payload_bytes, g.rho256, g.tau1024, g.max_depth, g.seed)

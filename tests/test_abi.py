@@ -9,6 +9,7 @@ import pytest
 
 ROOT = Path(__file__).resolve().parent.parent
 INCLUDE = ROOT / "include"
+SYNTH_INCLUDE = ROOT / "standin" / "include"
 
 
 @pytest.fixture(scope="module")
@@ -21,6 +22,17 @@ def built():
     return _abi
 
 
+@pytest.fixture(scope="module")
+def standin():
+    """The synthetic stand-in's library (test / bench infrastructure; its own package, standin/)."""
+    from standin import build
+
+    build.build()
+    from standin import abi
+
+    return abi
+
+
 def declared_functions(header: Path):
     text = re.sub(r"/\*.*?\*/", "", header.read_text(), flags=re.S)
     text = re.sub(r"//[^\n]*", "", text)
@@ -30,22 +42,22 @@ def declared_functions(header: Path):
     return names
 
 
-def test_headers_declare_what_ctypes_binds(built):
+def test_headers_declare_what_ctypes_binds(built, standin):
     abi = declared_functions(INCLUDE / "tz_abi.h") | declared_functions(INCLUDE / "tz_replay.h")
-    synth = declared_functions(INCLUDE / "tz_synth.h") - abi
+    synth = declared_functions(SYNTH_INCLUDE / "tz_synth.h") - abi
     assert abi == set(built.TZ_SYMBOLS), abi ^ set(built.TZ_SYMBOLS)
     synth_exported = {n for n in synth if not n.startswith(("tz_synth_init_h", "tz_synth_step_h", "tz_synth_legal", "tz_synth_logit",
                                                             "tz_synth_terminal", "tz_synth_reward", "tz_synth_value",
                                                             "tz_synth_payload_word"))}
-    assert synth_exported == set(built.TZ_SYNTH_SYMBOLS), synth_exported ^ set(built.TZ_SYNTH_SYMBOLS)
+    assert synth_exported == set(standin.TZ_SYNTH_SYMBOLS), synth_exported ^ set(standin.TZ_SYNTH_SYMBOLS)
 
 
-def test_libraries_export_every_declared_symbol(built):
+def test_libraries_export_every_declared_symbol(built, standin):
     lib = C.CDLL(str(built.LIB_DIR / "libtz_b200.so"))
     for name in declared_functions(INCLUDE / "tz_abi.h") | declared_functions(INCLUDE / "tz_replay.h"):
         assert hasattr(lib, name), f"libtz_b200.so does not export {name}"
-    synth = C.CDLL(str(built.LIB_DIR / "libtz_synth.so"))
-    for name in built.TZ_SYNTH_SYMBOLS:
+    synth = C.CDLL(str(standin.LIB_DIR / "libtz_synth.so"))
+    for name in standin.TZ_SYNTH_SYMBOLS:
         assert hasattr(synth, name), f"libtz_synth.so does not export {name}"
     out = subprocess.run(["nm", "-D", "--defined-only", str(built.LIB_DIR / "libtz_b200.so")], capture_output=True, text=True).stdout
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
@@ -57,6 +69,15 @@ def test_product_library_does_not_depend_on_oracle_or_synth(built):
     assert "oracle" not in out and "tz_synth" not in out
 
 
+def test_product_package_does_not_import_the_stand_in_or_the_oracle():
+    """turbozero_b200 (the product) must not reach into standin/ (bench / test stand-in) or oracle/ (the checker)."""
+    pkg = ROOT / "turbozero_b200"
+    for f in pkg.glob("*.py"):
+        text = f.read_text()
+        assert not re.search(r"^\s*(from|import)\s+(standin|oracle)\b", text, flags=re.M), f"{f.name} imports test infrastructure"
+    assert not (pkg / "synthetic.py").exists()
+
+
 def test_abi_version_and_strerror(built):
     lib = built.lib()
     assert lib.tz_abi_version() == built.TZ_ABI_VERSION == 7
@@ -65,7 +86,7 @@ def test_abi_version_and_strerror(built):
     assert b"not supported" in lib.tz_strerror(-2)
 
 
-def test_struct_layouts_match_the_c_compiler(built, tmp_path):
+def test_struct_layouts_match_the_c_compiler(built, standin, tmp_path):
     src = tmp_path / "layout.c"
     src.write_text(r'''
 #include <stdio.h>
@@ -79,10 +100,10 @@ int main(void) {
   return 0;
 }''')
     exe = tmp_path / "layout"
-    subprocess.run(["gcc", f"-I{INCLUDE}", str(src), "-o", str(exe)], check=True)
+    subprocess.run(["gcc", f"-I{INCLUDE}", f"-I{SYNTH_INCLUDE}", str(src), "-o", str(exe)], check=True)
     lines = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
     T, S, W = built.TzTree, built.TzSearchCfg, built.TzWork
-    assert lines[0].split() == [str(C.sizeof(x)) for x in (T, S, W, built.TzSynthGame, built.TzSynthCtx)]
+    assert lines[0].split() == [str(C.sizeof(x)) for x in (T, S, W, standin.TzSynthGame, standin.TzSynthCtx)]
     assert lines[1].split() == [str(getattr(T, f).offset) for f in ("next_free_idx", "child_stats", "best", "sel_state", "emb", "emb_row_bytes", "stats")]
     assert lines[2].split() == [str(getattr(S, f).offset) for f in ("discount", "inv_q_temperature", "fma_backup", "programmatic", "q_transform", "sim_warps")]
     assert lines[3].split() == [str(getattr(W, f).offset) for f in ("emb_parent", "policy", "emb_new", "path", "path_spill", "path_spill_cap", "timeline_slots", "timeline")]

@@ -259,7 +259,7 @@ def test_2048_step_with_replay_update_at_bench_shape():
     import turbozero_b200 as tz
     from helpers import make_cuda_evaluator
     from oracle import replay_numpy as RN
-    from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay
+    from standin.synthetic import SyntheticGame, SyntheticSelfPlay
 
     B, F, cap, moves = 2048, 4, 16, 3
     s = Schedule(game=SN.make_game("2048", 5001), B=B, N=200, S=100, moves=moves, temperature=1.0, discount=1.0, programmatic=True)
@@ -323,7 +323,7 @@ def test_masked_reset_touches_only_the_flagged_trees():
     """MCTS.reset(state, mask): Tree.reset (tree.py:272-278) for the flagged trees, the others bit-for-bit untouched."""
     import torch
     from helpers import make_cuda_evaluator, tree_to_numpy
-    from turbozero_b200.synthetic import SyntheticGame
+    from standin.synthetic import SyntheticGame
 
     s = Schedule(**CASES["c4"])
     g = s.game
@@ -352,7 +352,7 @@ def test_launch_timeline_records_every_search_and_leaf_launch():
     """TzWork.timeline / tz_synth_set_timeline (what bench.py's roofline leg reads): every launch of a replayed move writes
     its row, rows are ordered in time, and the trees are the oracle's with the record on."""
     import torch
-    from turbozero_b200.synthetic import SyntheticGame, SyntheticSelfPlay
+    from standin.synthetic import SyntheticGame, SyntheticSelfPlay
     from helpers import make_cuda_evaluator, tree_to_numpy
 
     for programmatic in (False, True):
@@ -436,7 +436,7 @@ def test_cta_per_tree_rebuilds_a_foreign_path_record():
     other form is not trusted; the kernel rebuilds the path from parents[] / edge_map -- same trees as the oracle."""
     import torch
     from helpers import make_cuda_evaluator, tree_to_numpy
-    from turbozero_b200.synthetic import SyntheticGame
+    from standin.synthetic import SyntheticGame
 
     for name in ("c4", "go_muzero", "othello_weighted"):
         s = Schedule(**CASES[name])

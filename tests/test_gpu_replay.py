@@ -119,7 +119,7 @@ def test_collect_step_glue_vs_oracle():
     same per-step records."""
     import torch
     import turbozero_b200 as tz
-    from turbozero_b200.synthetic import SyntheticEnv, SyntheticGame, make_synthetic_evaluator
+    from standin.synthetic import SyntheticEnv, SyntheticGame, make_synthetic_evaluator
 
     B, cap, F, moves = 48, 8, 7, 12
     game = SyntheticGame(F, 12, 230, 120, 7, 91)

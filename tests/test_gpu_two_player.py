@@ -20,7 +20,7 @@ CASES = {
 def _play_group(name, games, p1_first, fx):
     import torch
     import turbozero_b200 as tz
-    from turbozero_b200.synthetic import SyntheticEnv, SyntheticGame, make_synthetic_evaluator
+    from standin.synthetic import SyntheticEnv, SyntheticGame, make_synthetic_evaluator
 
     gkw, e1, e2, max_steps = CASES[name]
     g = SN.SynthGame(**gkw)
@@ -100,7 +100,7 @@ def test_two_player_game_driver_runs_to_completion():
     """two_player_game (common.py:235-367) end to end with random noise: games complete, outcomes are frozen once set."""
     import torch
     import turbozero_b200 as tz
-    from turbozero_b200.synthetic import SyntheticEnv, SyntheticGame, make_synthetic_evaluator
+    from standin.synthetic import SyntheticEnv, SyntheticGame, make_synthetic_evaluator
 
     game = SyntheticGame(7, 8, 230, 200, 6, 77)
     G = 32

@@ -65,17 +65,6 @@ class TzReplay(C.Structure):
     ]
 
 
-class TzSynthGame(C.Structure):
-    _fields_ = [
-        ("F", C.c_int32), ("payload_bytes", C.c_int32), ("rho256", C.c_int32), ("tau1024", C.c_int32),
-        ("max_depth", C.c_int32), ("seed", C.c_uint32),
-    ]
-
-
-class TzSynthCtx(C.Structure):
-    _fields_ = [("game", TzSynthGame), ("B", C.c_int32)]
-
-
 LEAF_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(TzWork), C.c_void_p)
 
 _P = C.POINTER
@@ -106,28 +95,12 @@ TZ_SYMBOLS = {
     "tz_replay_gather": (C.c_int, [_P(TzReplay), _vp, C.c_int, _P(_vp), _vp]),
 }
 
-TZ_SYNTH_SYMBOLS = {
-    "tz_synth_launch_count": (C.c_uint64, []),
-    "tz_synth_init_states": (C.c_int, [_P(TzSynthGame), C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
-    "tz_synth_root": (C.c_int, [_P(TzSynthGame), C.c_int, _vp, _vp, C.c_float, _vp, _vp, _vp]),
-    "tz_synth_leaf": (C.c_int, [_P(TzSynthGame), C.c_int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "tz_synth_env_step": (C.c_int, [_P(TzSynthGame), C.c_int, C.c_int, _vp, _vp, _vp, _vp, _vp, _vp]),
-    "tz_synth_leaf_cb": (C.c_int, [_vp, C.c_int, _P(TzWork), _vp]),
-    "tz_synth_timed_begin": (C.c_int, [C.c_int]),
-    "tz_synth_leaf_cb_timed": (C.c_int, [_vp, C.c_int, _P(TzWork), _vp]),
-    "tz_synth_timed_collect": (C.c_int, [_vp, _vp]),
-    "tz_synth_set_programmatic": (C.c_int, [C.c_int]),
-    "tz_synth_set_timeline": (C.c_int, [_vp, C.c_int]),
-    "tz_synth_leaf_seq": (C.c_uint64, []),
-}
-
-
 class TzError(RuntimeError):
     pass
 
 
-def _load(name: str, symbols) -> C.CDLL:
-    path = LIB_DIR / name
+def _load(name: str, symbols, lib_dir: Path = None) -> C.CDLL:
+    path = (lib_dir or LIB_DIR) / name
     if not path.exists():
         raise TzError(
             f"{path} is missing: build it with `python -m turbozero_b200.build` (needs nvcc). "
@@ -141,7 +114,6 @@ def _load(name: str, symbols) -> C.CDLL:
 
 
 _lib = None
-_synth = None
 
 
 def lib() -> C.CDLL:
@@ -153,14 +125,6 @@ def lib() -> C.CDLL:
         if _lib.tz_abi_version() != TZ_ABI_VERSION:
             raise TzError("libtz_b200.so ABI version mismatch")
     return _lib
-
-
-def synth_lib() -> C.CDLL:
-    """libtz_synth.so: the synthetic game stand-in (bench / tests only)."""
-    global _synth
-    if _synth is None:
-        _synth = _load("libtz_synth.so", TZ_SYNTH_SYMBOLS)
-    return _synth
 
 
 def check(rc: int, what: str) -> None:

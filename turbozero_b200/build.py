@@ -1,6 +1,6 @@
 """In-tree build of the CUDA libraries (nvcc cross-compiles sm_100a without a GPU).
 
-    python -m turbozero_b200.build            # libtz_b200.so + libtz_synth.so into turbozero_b200/lib/
+    python -m turbozero_b200.build            # libtz_b200.so into turbozero_b200/lib/
 
 The built .so files are git-ignored but travel to the GPU box with the gpurun snapshot.
 """
@@ -32,7 +32,6 @@ TARGETS = {
     "libtz_b200.so": ["csrc/tz_kernels.cu", "csrc/tz_replay.cu", "csrc/tz_reroot.cu", "csrc/tz_sim_nc1.cu", "csrc/tz_sim_nc2.cu",
                       "csrc/tz_sim_nc3.cu", "csrc/tz_sim_nc4.cu", "csrc/tz_sim_nc8.cu", "csrc/tz_sim_nc16.cu",
                       "csrc/tz_wide_plain.cu", "csrc/tz_wide_weighted.cu"],
-    "libtz_synth.so": ["csrc/tz_synth.cu"],
 }
 
 

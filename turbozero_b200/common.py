@@ -72,7 +72,9 @@ def step_env_and_evaluator(
     env_state, env_state_metadata = env_step_fn(env_state, output.action)
     terminated = env_state_metadata.terminated.bool()
     truncated = env_state_metadata.step > max_steps  # strict, common.py:86
-    rewards = env_state_metadata.rewards.clone()  # an env_init_fn that resets metadata in place must not change them
+    rewards = env_state_metadata.rewards
+    if reset and env_init_fn is not None:
+        rewards = rewards.clone()  # an env_init_fn that resets metadata in place must not change what is returned
     done = terminated | truncated
     if reset:
         eval_state = evaluator.step(output.eval_state, output.action, reset_mask=done)

@@ -347,7 +347,12 @@ class MCTS(Evaluator):
         """mcts.py:399-414.  `reset_mask` folds the caller's reset-vs-step select (core/common.py:89-94) into the
         same launch: flagged trees are reset instead of re-rooted; `keep_mask` trees are left untouched."""
         flags = None
-        if reset_mask is not None or keep_mask is not None:
+        if reset_mask is not None and keep_mask is None:
+            # the common case (core/common.py:89-94 with reset=True): a bool / uint8 mask IS the flag byte (1 = reset)
+            rm = reset_mask
+            flags = rm.view(torch.uint8) if rm.dtype == torch.bool else (rm != 0).view(torch.uint8)
+            flags = flags.reshape(state.batch_size).contiguous()
+        elif reset_mask is not None or keep_mask is not None:
             flags = torch.zeros((state.batch_size,), dtype=torch.uint8, device=state.device)
             if reset_mask is not None:
                 flags = torch.where(reset_mask.bool(), 1, flags.int()).to(torch.uint8)
