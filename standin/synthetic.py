@@ -301,7 +301,7 @@ class SyntheticEnv:
     ends re-initialises it in the same launch (common.py:95-100) and reports `terminated` for that step."""
 
     def __init__(self, game: SyntheticGame, B: int, env_offset: int = 0, device="cuda"):
-        from .types import StepMetadata
+        from turbozero_b200.types import StepMetadata
 
         self._md = StepMetadata
         self.game, self.B, self.env_offset = game, B, env_offset
