@@ -245,9 +245,11 @@ def run_reference(args, out):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32+i32", "data": "synthetic",
-        "config": {"workload": desc, "envs_per_gpu": B, "envs": B, "simulations": S, "max_nodes": N, "branching_factor": g.F,
-                   "embedding_bytes": g.payload_bytes + 16, "note": "reference algorithm on host CPU via the oracle port "
-                   "(oracle/tz_oracle.c); the reference itself needs JAX, which is not installable in this image"},
+        "config": {"workload": desc, "envs_per_gpu": B, "envs_total": B, "simulations": S, "max_nodes": N, "branching_factor": g.F,
+                   "embedding_bytes": g.payload_bytes + 16, "weighted": weighted, "discount": discount,
+                   "note": "reference algorithm on host CPU via the oracle port (oracle/tz_oracle.c, OpenMP over trees); the "
+                           "reference itself needs JAX, which is not installable in this image.  One host runs ONE per-GPU "
+                           "workload whatever --gpus says (rank 0 only)"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,

@@ -654,8 +654,23 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
       uint8_t* const st = stage + d.st_off;
       const uint32_t rb = d.rb;
       switch (d.code) {
-        case TD_BULK:  // one bulk copy per row
-          for (int r = lane; r < rows; r += 32) bulk_g2s(st + (size_t)r * rb, d.base + (size_t)src_of[s0 + r] * rb, rb, &bar);
+        case TD_BULK:  // one bulk copy per RUN of adjacent source rows (their destinations are adjacent by construction): the
+                       // bulk-copy unit takes ~3 ns per copy whatever its size, and nodes allocated by consecutive simulations
+                       // into the same subtree are neighbours
+          for (int r0 = 0; r0 < rows; r0 += 32) {
+            const int r = r0 + lane;
+            const bool in = r < rows;
+            const int srow = in ? src_of[s0 + r] : -2;
+            const int prev = __shfl_up_sync(FULL, srow, 1);
+            const bool start = in && (lane == 0 || prev != srow - 1);
+            const unsigned starts = __ballot_sync(FULL, start);
+            const unsigned inmask = __ballot_sync(FULL, in);
+            if (start) {
+              const unsigned above = starts & ~((2u << lane) - 1u);                    // runs that start above this lane
+              const int end = above ? __ffs(above) - 1 : 32 - __clz(inmask);           // first lane past this run
+              bulk_g2s(st + (size_t)r * rb, d.base + (size_t)srow * rb, (unsigned)(end - lane) * rb, &bar);
+            }
+          }
           break;
         case TD_N4:
           for (int r = lane; r < rows; r += 32) cp_async4(st + 4 * (size_t)r, d.base + 4 * (size_t)src_of[s0 + r]);
