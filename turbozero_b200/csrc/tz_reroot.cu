@@ -971,13 +971,15 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
         if (tb.kind < 4) off += ((size_t)P.rpc * tb.pad + 15) & ~(size_t)15;
       }
       const size_t smem = (size_t)stage + 8 * (size_t)t->N + (size_t)pre_bytes;
-      const bool big = ctas <= 3;  // few CTAs per SM: 512 threads each (pointer jumping and the scan over up to N nodes, the scatter)
-      auto kernel = big ? k_reroot_bulk<512> : k_reroot_bulk<128>;
+      // threads per CTA by CTAs per SM (pointer jumping and the scan over up to N nodes, the child_stats pass of the scatter):
+      // 512 when at most 3 CTAs share an SM, 256 up to 5, else 128
+      const int nthreads = ctas <= 3 ? 512 : (ctas <= 5 ? 256 : 128);
+      auto kernel = nthreads == 512 ? k_reroot_bulk<512> : (nthreads == 256 ? k_reroot_bulk<256> : k_reroot_bulk<128>);
       if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
       }
-      kernel<<<t->B, big ? 512 : 128, smem, (cudaStream_t)stream>>>(P, action, reset_flag, persist_tree);
+      kernel<<<t->B, nthreads, smem, (cudaStream_t)stream>>>(P, action, reset_flag, persist_tree);
       return launch_status();
     }
     for (int k = 0; k < nt; ++k) {  // (fall through to the one-table-at-a-time kernel below with the original descriptors)
