@@ -497,8 +497,10 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
                     traffic = float(json.load(f)["traffic_bytes_per_launch"])
             except Exception:
                 traffic = None
-        roofline = {"bound": "hbm", "kernel": "k_sim (expand+backprop of simulation i fused with select of i+1): the instantiation "
-                    "the headline step runs, timed inside a replay of that step (first warp in -> last warp out, %globaltimer)",
+        wide = args.sim_warps > 1 or (args.sim_warps == 0 and F > 32)
+        kname = (f"k_sim_wide (a CTA of {args.sim_warps or (2 if weighted else 4)} warps per tree)" if wide else "k_sim (one warp per tree)")
+        roofline = {"bound": "hbm", "kernel": kname + ": expand+backprop of simulation i fused with select of i+1, the instantiation "
+                    "this step runs, timed inside a replay of the step (first warp in -> last warp out, %globaltimer)",
                     "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                     "traffic_source": "profiles/ksim_traffic.json (ncu --set full, cold L2)" if traffic else None,
                     "peak_source": peak_src, "avg_launch_us": dur_us, "median_launch_us": statistics.median(resident) * 1e-3 if resident else None,
@@ -530,7 +532,7 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         rr_bytes = (4 * int(rr_st[2]) + R_row * (int(rr_st[3]) + int(rr_st[2]))) / moves_r
         rr_avg_ms = sum(rr_ms) / len(rr_ms)
         rr_achieved = rr_bytes / (rr_avg_ms * 1e-3) / 1e9
-        roofline["reroot"] = {"bound": "hbm", "kernel": "k_reroot_all (get_subtree / reset of every tree, one launch per move)",
+        roofline["reroot"] = {"bound": "hbm", "kernel": "k_reroot_bulk (get_subtree / reset of every tree, one launch per move)",
                               "achieved": rr_achieved, "peak": peak, "unit": "GB/s", "frac": rr_achieved / peak,
                               "avg_launch_us": rr_avg_ms * 1e3, "algorithmic_bytes_per_launch": rr_bytes,
                               "rows_before": int(rr_st[2]) / moves_r / B, "rows_kept": int(rr_st[3]) / moves_r / B}
