@@ -215,8 +215,16 @@ class EpisodeReplayBuffer:
         mine = owner == rank
         rows = self.gather(state, torch.where(mine, local, torch.zeros_like(local)))
         leaves = _flatten(rows)
-        for t in leaves:  # zero the rows other ranks own, then sum over ranks (bytes add up because ownership is disjoint)
-            t[~mine] = 0
-            work = t.view(torch.uint8) if t.dtype == torch.bool else t
-            dist.all_reduce(work, op=dist.ReduceOp.SUM, group=group)
+        # zero the rows other ranks own, then sum over ranks (bytes add up because ownership is disjoint).  All leaves travel as ONE
+        # byte buffer -> one all-reduce per sample instead of one per leaf; masked_fill instead of boolean indexing: no host sync
+        k = int(local.numel())
+        views = [(t.view(torch.uint8) if t.dtype == torch.bool else t).reshape(k, -1).view(torch.uint8) for t in leaves]
+        widths = [int(v.shape[1]) for v in views]
+        packed = torch.cat(views, dim=1)
+        packed.masked_fill_(~mine.unsqueeze(1), 0)
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        off = 0
+        for t, v, w in zip(leaves, views, widths):
+            v.copy_(packed[:, off:off + w])
+            off += w
         return rows
