@@ -62,10 +62,12 @@ TZ_HD uint32_t tz_float_to_bits(float f) {
 #endif
 }
 
-/* exp(x) for x <= ~88.  x < -86 flushes to +0 (keeps 2^k normal). */
+/* exp(x) for x <= ~88.  x < -86 flushes to +0 (keeps 2^k normal).  Written without an early return: straight-line code,
+ * so that independent calls interleave on the device instead of running one after the other behind a branch each. */
 TZ_HD float tz_expf(float x) {
-  if (x < -86.0f) return 0.0f;
+  const int flush = x < -86.0f;
   if (x > 88.0f) x = 88.0f;
+  if (flush) x = -86.0f; /* (any in-range argument: the result is discarded) */
   float k = TZ_RINT(TZ_MUL(x, 1.44269504088896341f));
   float r = TZ_SUB(x, TZ_MUL(k, 0.693359375f));
   r = TZ_SUB(r, TZ_MUL(k, -2.12194440e-4f));
@@ -82,7 +84,8 @@ TZ_HD float tz_expf(float x) {
   int k1 = ki / 2, k2 = ki - k1;
   float s1 = tz_bits_to_float((uint32_t)(k1 + 127) << 23);
   float s2 = tz_bits_to_float((uint32_t)(k2 + 127) << 23);
-  return TZ_MUL(TZ_MUL(y, s1), s2);
+  const float res = TZ_MUL(TZ_MUL(y, s1), s2);
+  return flush ? 0.0f : res;
 }
 
 /* log(x) for normal x > 0.  x < FLT_MIN is treated as FLT_MIN. */

@@ -176,6 +176,31 @@ static void traverse(const View* v, const TzSearchCfg* cfg, int* parent_out, int
   *levels_out = levels;
 }
 
+#ifdef TZO_TRACE
+/* histogram over simulations of (path length L, first level d at which the walk's node differs from the previous walk's),
+   both clamped to 255; per thread: the previous path */
+EXPORT long long tzo_trace_hist[256][256];
+static __thread int trace_prev[4096], trace_prev_len;
+static void tzo_trace_walk(const View* v, int parent, int levels, int first) {
+  int cur[4096], L = levels < 4096 ? levels : 4096, x = parent;
+  for (int l = L - 1; l >= 0 && x >= 0; --l) {
+    cur[l] = x;
+    x = v->parents[x];
+  }
+  int d = 0;
+  if (!first)
+    while (d < L && d < trace_prev_len && cur[d] == trace_prev[d]) ++d;
+  /* d = levels shared with the previous walk (level 0, the root, is always shared) */
+  if (!first) {
+    int pl = trace_prev_len < 255 ? trace_prev_len : 255, dd = d < 255 ? d : 255;
+#pragma omp atomic
+    tzo_trace_hist[pl][dd] += 1;
+  }
+  for (int l = 0; l < L; ++l) trace_prev[l] = cur[l];
+  trace_prev_len = L;
+}
+#endif
+
 /* mcts.py:174-187 + tree.py:101-132,153-166 */
 static void expand(View* v, int parent, int action, const float* policy, float value, uint8_t term,
                    void* const* new_emb, int b, const TzSearchCfg* cfg) {
@@ -600,6 +625,9 @@ EXPORT int tzo_selfplay(const TzTree* t, const TzSearchCfg* cfg, const TzSynthGa
         for (int s = 0; s < num_iterations; ++s) {
           int parent, action, levels;
           traverse(&v, cfg, &parent, &action, &levels);
+#ifdef TZO_TRACE /* diagnostic build (scripts/trace_divergence.py): where does a walk leave the previous one? */
+          tzo_trace_walk(&v, parent, levels, s == 0);
+#endif
           float val;
           uint8_t term;
           const int32_t* pcore = (const int32_t*)(v.emb[0] + (size_t)parent * 16);
