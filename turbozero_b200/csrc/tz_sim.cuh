@@ -326,12 +326,8 @@ __global__ void __launch_bounds__(SIM_THREADS) k_sim(const __grid_constant__ Sim
                 pq = __shfl_sync(FULL, q1, (lvl + 1) & 31);
                 pnb = __shfl_sync(FULL, n1, (lvl + 1) & 31);
               }
-              if (lvl < top || node >= 0) patch_stats<NC>(rows[u], a_here, lane, pq, pnb);
-              if (lvl == top && node >= 0 && lane == (a_here & 31)) {
-#pragma unroll
-                for (int c = 0; c < NC; ++c)
-                  if (c == (a_here >> 5)) rows[u].e[c] = node;
-              }
+              patch_stats<NC>(rows[u], a_here, lane, pq, pnb, lvl < top || node >= 0);
+              patch_edge<NC>(rows[u], a_here, lane, node, lvl == top && node >= 0);
               if (WEIGHTED) {  // weighted_mcts.py:102-142
                 const float qX = __shfl_sync(FULL, qd, sl), rX = __shfl_sync(FULL, rd, sl);
                 const int nX = __shfl_sync(FULL, nd, sl);

@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
           const int2 r = s_rec[jj];
           nxt = row;
           if (jj >= 1) load_row<NC, false>(tv, s_rec[jj - 1].x, lane, nxt);
-          if (lo + jj < top || node >= 0) patch_stats<NC>(row, r.y, lane, bq, bn);
+          patch_stats<NC>(row, r.y, lane, bq, bn, lo + jj < top || node >= 0);
           const float qX = s_q1[jj], rX = s_r[jj];
           const int nX = s_n1[jj];
           const float qw = weighted_value<NC>(row, F, cfg, qX, lane, noise);  // weighted_mcts.py:102-137
@@ -344,12 +344,8 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
             pnb = s_n1[j + 1];
           }
           const bool is_top = lo + j == top;
-          if (!is_top || node >= 0) patch_stats<NC>(row, r.y, lane, pq, pnb);
-          if (is_top && node >= 0 && lane == (r.y & 31)) {
-#pragma unroll
-            for (int c = 0; c < NC; ++c)
-              if (c == (r.y >> 5)) row.e[c] = node;
-          }
+          patch_stats<NC>(row, r.y, lane, pq, pnb, !is_top || node >= 0);
+          patch_edge<NC>(row, r.y, lane, node, is_top && node >= 0);
           const int2 e = select_entry<NC, SEL>(row, F, cfg, s_q1[j], s_n1[j], lane);
           if (lane == 0) {
             s_best[j] = e;
