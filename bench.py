@@ -58,9 +58,11 @@ METRIC = "mcts_simulations_per_sec"
 UNIT = "simulations/s"
 
 # name -> (synthetic game shape, envs per GPU at the config's GPU count, simulations, max_nodes, weighted, discount, description)
-# Programmatic dependent launches (TzSearchCfg.programmatic) are on by default except for the go_9x9 shape, whose leaf
-# stand-in runs long enough that a waiting search grid costs more than the overlap saves (profiles/r1h_pdl_modes.log).
-NO_PDL_BY_DEFAULT = {"cfg4"}
+# Programmatic dependent launches (TzSearchCfg.programmatic) pay on the narrow shallow shapes (configs[0..1]: +16 %); on the
+# go_9x9 shape the leaf stand-in runs long enough that a waiting search grid costs more than the overlap saves
+# (profiles/r1h_pdl_modes.log), and on the othello / 2048 shapes ordinary launches measured 3-5 % faster
+# (profiles/r2z_bench.log, r2aa_bench.log: 27.3 vs 26.1 M and 172.4 vs 168.0 M simulations/s).
+NO_PDL_BY_DEFAULT = {"cfg3", "cfg4", "cfg5"}
 REPLAY_CAPACITY = 256  # slots per env of the episode replay buffer in the cfg5 step
 TRAIN_BATCH = 1024     # rows of the cross-rank replay sample per step (cfg5, N > 1)
 GRAD_FLOATS = 2 << 20  # parameter-sized buffer of the gradient-mean all-reduce (cfg5, N > 1): 2 Mi fp32 = 8 MiB

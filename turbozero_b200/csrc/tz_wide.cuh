@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
           if (lane == 0) {
             s_q1[jj] = q1;
             s_n1[jj] = nX + 1;
-            __threadfence_block();
+            asm volatile("fence.acq_rel.cta;" ::: "memory");  // release: the two stores above before the flag below
             s_done = cnt - jj;
             tv.q[r.x] = q1;
             tv.n[r.x] = nX + 1;
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
           if (j - SW >= 0) load_row<NC, true>(tv, s_rec[j - SW].x, lane, nxt);
           if (WEIGHTED && W > 1) {
             while (s_done < cnt - j) { }  // the chain has published this level (and the one below it)
-            __threadfence_block();
+            asm volatile("fence.acq_rel.cta;" ::: "memory");  // acquire
           }
           float pq;
           int pnb;
