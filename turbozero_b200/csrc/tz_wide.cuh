@@ -107,6 +107,7 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
   __shared__ int2 s_best[WIN];   // the level's new selector decision (best-table entry)
   __shared__ int s_wmin[W];
   __shared__ int s_walk[2];
+  __shared__ uint64_t s_bar;       // completion of the staged best-table's bulk copy
   __shared__ volatile int s_done;  // weighted: levels of this pass whose backup is published, counted from the deepest
   extern __shared__ __align__(16) uint8_t wide_smem[];  // the tree's best-table, staged for the walk (P.best_rows > 0)
   const int b = blockIdx.x;
@@ -145,8 +146,9 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
       for (int c = 0; c < NC; ++c) pol[c] = (c * 32 + lane < F) ? P.w_policy[(size_t)b * F + c * 32 + lane] : 0.0f;
     }
   }
+  bool stale;
   {  // the best-table is only valid for the selector parameters it was computed with
-    const bool stale = s0.x != cfg.selector || s0.y != __float_as_int(cfg.c) || s0.z != __float_as_int(cfg.c1) ||
+    stale = s0.x != cfg.selector || s0.y != __float_as_int(cfg.c) || s0.z != __float_as_int(cfg.c1) ||
                        s0.w != __float_as_int(cfg.c2) || s1.x != __float_as_int(cfg.epsilon) ||
                        s1.y != __float_as_int(cfg.discount) || s1.z != cfg.q_transform;
     if (stale) {  // (uniform over the CTA)
@@ -162,16 +164,32 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
   // stage the best-table for the walk (fire-and-forget global -> shared copies; they land while the backup runs): the walk's
   // remainder is then one shared-memory load per level instead of one dependent L2 / DRAM round trip
   int2* const sb = (P.best_rows > 0 && do_sel) ? reinterpret_cast<int2*>(wide_smem) : nullptr;
+  // (one cp.async.bulk for the whole table when it is 16-byte aligned: the per-thread LDGSTS loop was 6 % of the kernel's
+  // instructions on the go_9x9 shape -- profiles/r2x_kwide_go_source.md; measured: go_9x9 unchanged, othello +1.7 %)
+  bool sb_bulk = false;
   if (sb != nullptr) {
     const int cnt = nfi + 1 < tv.N ? nfi + 1 : tv.N;
-    if ((((uintptr_t)tv.best) & 15) == 0) {
-      const int pairs = cnt >> 1;
-      for (int i = tid; i < pairs; i += NT) cp_async16(sb + 2 * i, tv.best + 2 * i);
-      if ((cnt & 1) && tid == 0) cp_async8(sb + cnt - 1, tv.best + cnt - 1);
+    sb_bulk = (((uintptr_t)tv.best) & 15) == 0 && cnt >= 2 && !stale;  // (a table this CTA has just rewritten: generic copies)
+    if (sb_bulk) {
+      if (tid == 0) {
+        const unsigned bytes = (unsigned)(cnt >> 1) * 16u;
+        mbar_init(&s_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&s_bar, bytes);
+        bulk_g2s(sb, tv.best, bytes, &s_bar);
+        if (cnt & 1) cp_async8(sb + cnt - 1, tv.best + cnt - 1);
+      }
     } else {
       for (int i = tid; i < cnt; i += NT) cp_async8(sb + i, tv.best + i);
     }
   }
+  // every thread, before it reads the staged table (a barrier follows at both call sites)
+  auto staged_wait = [&]() {
+    cp_async_wait_all();
+    if (sb_bulk) {
+      if (tid == 0) mbar_wait(&s_bar, 0);  // (the others pass the barrier after thread 0 has seen the copy complete)
+    }
+  };
   int L = 0;             // length of the path this expansion hangs from (levels 0 .. L-1)
   int fresh_node = -1;   // row written by this launch's expand
   if (do_expand) {
@@ -291,7 +309,7 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
         }
       }
       if (tid == 0) s_done = 0;
-      if (first_pass && sb != nullptr) cp_async_wait_all();  // this thread's share of the staged best-table has landed
+      if (first_pass && sb != nullptr) staged_wait();  // the staged best-table has landed
       __syncthreads();
       if (first_pass) TZ_WSTAMP(2);
       // -- B: one warp per level (weighted: warp 0 runs the backup chain, the others score behind it)
@@ -456,7 +474,7 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
   }
   TZ_WSTAMP(4);
   if (!do_expand && sb != nullptr) {  // select-only launch: nothing waited for the staged table yet
-    cp_async_wait_all();
+    staged_wait();
     __syncthreads();
   }
   if (warp == 0) {
