@@ -461,6 +461,18 @@ struct __align__(16) TabDesc {
   uint32_t kind : 4; // RerootTab.kind
 };
 
+__device__ __forceinline__ int ld_issue(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.b32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+
+template <typename K>
+inline int64_t static_shared_bytes(K kernel) {
+  cudaFuncAttributes a;
+  return cudaFuncGetAttributes(&a, kernel) == cudaSuccess ? (int64_t)a.sharedSizeBytes : 4096;
+}
+
 template <int NTHR>
 __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ RerootP P, const int32_t* __restrict__ action,
                                                                const uint8_t* __restrict__ reset_flag, const int persist_tree) {
@@ -468,6 +480,7 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   __shared__ int wsum[NTHR / 32];
   __shared__ __align__(8) uint64_t bar;
   __shared__ TabDesc s_td[REROOT_MAX_TABS];
+  __shared__ int s_edge[NTHR];  // the root's edge_map row (F <= NTHR)
   const int b = blockIdx.x;
   const int tid = threadIdx.x;
   constexpr int nthr = NTHR;
@@ -477,15 +490,38 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   int32_t* const src_of = trans + N;                                            // new index -> old index
 
   TZ_RSTAMP(0);
-  const int flag = reset_flag ? (int)reset_flag[b] : 0;
-  if (flag == 2) return;  // leave this tree untouched (core/common.py:91 `lambda s: s`)
-  const int nfi = P.nfi[b];
-  const bool do_reset = !persist_tree || flag != 0;
+  // Everything the ancestor test needs travels in ONE round trip: the reset flag, next_free_idx, the action, the root's
+  // edge_map row and the first PF strides of parents[] are all requested before the first of them is looked at (the flag
+  // test, then the action -> edge_map -> parents chain were three dependent round trips on every tree's critical path; rows
+  // beyond next_free_idx are initialised, reading them is harmless).
   const int32_t* const parents = P.parents + (size_t)b * N;
-  // edge_map[ROOT, action]; -1 -> nothing retained (tree.py:201-203).  Out-of-range actions clamp like an XLA gather.
-  const int c = do_reset ? -1 : P.edge[(size_t)b * N * F + min(max(action[b], 0), F - 1)];
-  int count = 0;
+  constexpr int PF = 4;
+  const bool edge_row = F <= NTHR;
+  // (ld_issue: a volatile load instruction -- the compiler would otherwise sink these loads below the early return)
+  const int flag = reset_flag ? (int)reset_flag[b] : 0;
+  const int nfi = ld_issue(P.nfi + b);
+  const int act_raw = (persist_tree && action) ? ld_issue(action + b) : 0;
+  int par_pre[PF];
+#pragma unroll
+  for (int k = 0; k < PF; ++k) par_pre[k] = (persist_tree && tid + k * nthr < N) ? ld_issue(parents + tid + k * nthr) : TZ_NULL_INDEX;
+  int my_edge = -1;
+  if (edge_row && persist_tree && tid < F) my_edge = ld_issue(P.edge + (size_t)b * N * F + tid);
+  if (flag == 2) return;  // leave this tree untouched (core/common.py:91 `lambda s: s`)
+  const bool do_reset = !persist_tree || flag != 0;
+  const int act = min(max(act_raw, 0), F - 1);  // out-of-range actions clamp like an XLA gather
+  if (edge_row) s_edge[tid] = my_edge;
   if (tid == 0) mbar_init(&bar, 1);
+  // edge_map[ROOT, action]; -1 -> nothing retained (tree.py:201-203)
+  int c = -1;
+  if (!do_reset) {  // (uniform over the CTA)
+    if (edge_row) {
+      __syncthreads();
+      c = s_edge[act];
+    } else {
+      c = P.edge[(size_t)b * N * F + act];
+    }
+  }
+  int count = 0;
   if (tid < P.ntab) {  // this tree's table descriptors (once per kernel; visible after the barriers below)
     const RerootTab& tb = P.tab[tid];
     TabDesc d;
@@ -510,7 +546,12 @@ __global__ void __launch_bounds__(NTHR) k_reroot_bulk(const __grid_constant__ Re
   TZ_RSTAMP(1);
   if (c >= 0) {
     // (1) ancestor test by pointer jumping (see k_reroot): Jacobi rounds between the two index arrays
-    for (int i = tid; i < nfi; i += nthr) trans[i] = (i == 0 || i == c) ? i : parents[i];
+#pragma unroll
+    for (int k = 0; k < PF; ++k) {
+      const int i = tid + k * nthr;
+      if (i < nfi) trans[i] = (i == 0 || i == c) ? i : par_pre[k];
+    }
+    for (int i = tid + PF * nthr; i < nfi; i += nthr) trans[i] = (i == 0 || i == c) ? i : parents[i];
     __syncthreads();
     int32_t* cur = trans;
     int32_t* nxt = src_of;
@@ -910,8 +951,13 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
     // bytes per second.  Measured on the go_9x9 shape: 3 rows per chunk at 7 CTAs per SM = 2.4 TB/s (profiles/r2d).
     int ctas = (t->B + 147) / 148;
     ctas = ctas < 1 ? 1 : (ctas > 7 ? 7 : ctas);
+    // (the kernels' static shared memory -- descriptors, the root's edge row -- counts against the SM like the dynamic part)
+    static const int64_t static_smem[3] = {static_shared_bytes(k_reroot_bulk<128>), static_shared_bytes(k_reroot_bulk<256>),
+                                           static_shared_bytes(k_reroot_bulk<512>)};
+    auto threads_for = [](int c) { return c <= 3 ? 512 : (c <= 5 ? 256 : 128); };
     auto stage_for = [&](int c) {
-      int64_t st = per_sm / c - 1024 - 640 - 8 * (int64_t)t->N - pre_bytes - 64;  // (1 KB per-CTA reserve, static shared memory, index scratch, preloaded tables)
+      const int64_t stat = static_smem[threads_for(c) == 128 ? 0 : (threads_for(c) == 256 ? 1 : 2)];
+      int64_t st = per_sm / c - 1024 - stat - 8 * (int64_t)t->N - pre_bytes - 64;  // (1 KB per-CTA reserve, static shared memory, index scratch, preloaded tables)
       st = st > 160 * 1024 ? 160 * 1024 : st;
       return st & ~(int64_t)15;
     };
@@ -943,7 +989,7 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
       const size_t smem = (size_t)stage + 8 * (size_t)t->N + (size_t)pre_bytes;
       // threads per CTA by CTAs per SM (pointer jumping and the scan over up to N nodes, the child_stats pass of the scatter):
       // 512 when at most 3 CTAs share an SM, 256 up to 5, else 128
-      const int nthreads = ctas <= 3 ? 512 : (ctas <= 5 ? 256 : 128);
+      const int nthreads = threads_for(ctas);
       auto kernel = nthreads == 512 ? k_reroot_bulk<512> : (nthreads == 256 ? k_reroot_bulk<256> : k_reroot_bulk<128>);
       if (smem > 48 * 1024) {
         const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
