@@ -20,12 +20,15 @@ B, F, N, S, MOVES = 6, 5, 40, 24, 4
 class ToyGame:
     """A batched two-player toy env in plain torch: state = {"x": float32[B, F], "t": int32[B], "player": int32[B]}."""
 
-    def __init__(self, torch):
+    def __init__(self, torch, F=F, value_scale=1.0):
         self.torch = torch
+        self.F = F
+        self.value_scale = value_scale  # multiplies every value / reward the search sees
         self.calls = []  # (kind, tensors...) in call order
 
     def init(self):
         t = self.torch
+        F = self.F
         g = t.Generator(device="cuda").manual_seed(3)
         # (keys in sorted order, so that insertion order == sorted order whichever the pytree flattening uses)
         return {"player": t.zeros((B,), dtype=t.int32, device="cuda"), "t": t.zeros((B,), dtype=t.int32, device="cuda"),
@@ -34,12 +37,13 @@ class ToyGame:
     def metadata(self, s, tz):
         t = self.torch
         term = (s["t"] >= 5) | (s["x"][:, 0] > 0.93)
-        r0 = t.where(s["x"][:, 1] > 0.5, 1.0, -1.0)
+        r0 = t.where(s["x"][:, 1] > 0.5, 1.0, -1.0) * self.value_scale
         return tz.StepMetadata(rewards=t.stack([r0, -r0], 1), action_mask=s["x"] > 0.12, terminated=term,
                                cur_player_id=s["player"].clone(), step=s["t"].clone())
 
     def make_step_fn(self, tz):
         t = self.torch
+        F = self.F
 
         def env_step_fn(state, action):  # core/types.py:27 (batched)
             a = action.long()
@@ -56,7 +60,7 @@ class ToyGame:
         t = self.torch
         x = env_state["x"]
         logits = t.sin(x * 3.7 + params) * 2.0
-        value = t.tanh(x[:, 0] * 1.3 - x[:, 1])
+        value = t.tanh(x[:, 0] * 1.3 - x[:, 1]) * self.value_scale
         self.calls.append(("eval", logits.clone(), value.clone()))
         return logits, value
 
@@ -69,24 +73,41 @@ def _emb_rows(state, b):
 def test_user_eval_and_env_functions_through_the_builtin_glue(programmatic):
     """`programmatic=True`: TzSearchCfg.programmatic with ordinary framework kernels between the launches (the first form of
     its contract) -- same trees."""
+    _run(programmatic=programmatic)
+
+
+@pytest.mark.parametrize("scale", [1e-22, 3e19, 1e-30])
+@pytest.mark.parametrize("shape", ["narrow", "wide_one_warp", "wide_cta", "weighted_one_warp", "weighted_cta"])
+def test_extreme_magnitudes_take_the_exact_division_path(shape, scale):
+    """Values of 1e-22 / 3e19 / 1e-30 put the selector's and the weighted backup's operands outside the range in which the
+    straight-line division (div_core) is proven equal to div.rn: the kernels must notice and repeat the call with the
+    hardware division -- same bits as the NumPy oracle on every path (one lane per level, one warp per tree, CTA per tree;
+    plain and weighted backups)."""
+    _run(F=5 if shape == "narrow" else 40, value_scale=scale, weighted=shape.startswith("weighted"),
+         sim_warps=4 if shape.endswith("cta") else 1, moves=3)
+
+
+def _run(programmatic=False, F=F, value_scale=1.0, weighted=False, sim_warps=0, moves=MOVES):
     import torch
     import turbozero_b200 as tz
 
-    game = ToyGame(torch)
+    game = ToyGame(torch, F, value_scale)
     step_fn = game.make_step_fn(tz)
-    ev = tz.AlphaZero(tz.MCTS)(eval_fn=game.eval_fn, action_selector=tz.PUCTSelector(c=1.25), branching_factor=F, max_nodes=N,
-                               num_iterations=S, discount=-1.0, temperature=1.0, dirichlet_alpha=0.3, dirichlet_epsilon=0.25)
+    base = tz.WeightedMCTS if weighted else tz.MCTS
+    ev = tz.AlphaZero(base)(eval_fn=game.eval_fn, action_selector=tz.PUCTSelector(c=1.25), branching_factor=F, max_nodes=N,
+                            num_iterations=S, discount=-1.0, temperature=1.0, dirichlet_alpha=0.3, dirichlet_epsilon=0.25)
     ev.programmatic_launch = programmatic
+    ev.sim_warps = sim_warps
     state = game.init()
     tree = ev.init_batched(B, {k: v[0] for k, v in state.items()})
     params = torch.tensor(0.2, device="cuda")
     gen = torch.Generator(device="cuda").manual_seed(11)
-    cfg = M.SearchCfg(selector=0, c=1.25, discount=-1.0)
+    cfg = M.SearchCfg(selector=0, c=1.25, discount=-1.0, weighted=weighted)
     emb_bytes = [int(np.prod(v.shape[1:])) * v.element_size() for k, v in sorted(state.items())]
-    ref = [M.init_tree(N, F, emb_bytes) for _ in range(B)]
+    ref = [M.init_tree(N, F, emb_bytes, weighted=weighted) for _ in range(B)]
     finfo = torch.finfo(torch.float32)
     md = game.metadata(state, tz)
-    for m in range(MOVES):
+    for m in range(moves):
         game.calls.clear()
         dn = torch._sample_dirichlet(torch.full((B, F), 0.3, device="cuda"), generator=gen)
         u01 = torch.rand((B,), device="cuda", generator=gen)
@@ -111,7 +132,10 @@ def test_user_eval_and_env_functions_through_the_builtin_glue(programmatic):
             for b in range(B):
                 parent, action, _ = M.traverse(ref[b], cfg)
                 M.expand(ref[b], parent, action, pol_n[b], np.float32(val_n[b]), bool(term_n[b]), _emb_rows(new_state, b), cfg)
-                M.backpropagate(ref[b], parent, np.float32(val_n[b]), cfg)
+                if weighted:
+                    M.weighted_backpropagate(ref[b], parent, cfg)
+                else:
+                    M.backpropagate(ref[b], parent, np.float32(val_n[b]), cfg)
         acts = out.action.cpu().numpy()
         pws = out.policy_weights.cpu().numpy()
         got = tree_to_numpy(tree)
