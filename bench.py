@@ -58,11 +58,13 @@ METRIC = "mcts_simulations_per_sec"
 UNIT = "simulations/s"
 
 # name -> (synthetic game shape, envs per GPU at the config's GPU count, simulations, max_nodes, weighted, discount, description)
-# Programmatic dependent launches (TzSearchCfg.programmatic) pay on the narrow shallow shapes (configs[0..1]: +16 %); on the
-# go_9x9 shape the leaf stand-in runs long enough that a waiting search grid costs more than the overlap saves
-# (profiles/r1h_pdl_modes.log), and on the othello / 2048 shapes ordinary launches measured 3-5 % faster
-# (profiles/r2z_bench.log, r2aa_bench.log: 27.3 vs 26.1 M and 172.4 vs 168.0 M simulations/s).
-NO_PDL_BY_DEFAULT = {"cfg3", "cfg4", "cfg5"}
+# Launch mode per shape, measured (profiles/r2ak_modes.log: ordinary / search launched programmatically / + the leaf stand-in
+# cooperating / + the search signalling its dependents early):
+#   connect_four 106.3 / 102.8 / 111.4 / 123.6 M   othello 28.0 / 27.8 / 26.4 / 26.5 M
+#   go_9x9       36.3 / 36.3 / 36.8 / 36.8 M        2048    174.3 / 170.6 / 182.0 / 168.0 M simulations/s
+# -> (TzSearchCfg.programmatic bits, leaf stand-in cooperates) per workload; None = ordinary stream-ordered launches, the API default.
+PDL_MODE = {"cfg1": (3, 1), "cfg2": (3, 1), "cfg3": None, "cfg4": (1, 1), "cfg5": (1, 1)}
+NO_PDL_BY_DEFAULT = {w for w, m in PDL_MODE.items() if m is None}
 REPLAY_CAPACITY = 256  # slots per env of the episode replay buffer in the cfg5 step
 TRAIN_BATCH = 1024     # rows of the cross-rank replay sample per step (cfg5, N > 1)
 GRAD_FLOATS = 2 << 20  # parameter-sized buffer of the gradient-mean all-reduce (cfg5, N > 1): 2 Mi fp32 = 8 MiB
@@ -89,6 +91,10 @@ def parse_args():
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-pdl", action="store_true", help="ordinary stream-ordered launches (TzSearchCfg.programmatic = 0)")
     ap.add_argument("--pdl", action="store_true", help="force programmatic dependent launches on")
+    ap.add_argument("--pdl-bits", type=int, default=0, help="TzSearchCfg.programmatic when programmatic launches are on (1: launch "
+                    "programmatically; 3: also signal dependents early; 0: the workload's measured best, PDL_MODE)")
+    ap.add_argument("--leaf-pdl", type=int, default=-1, help="the stand-in leaf kernel cooperates (waits, then signals) when "
+                    "programmatic launches are on; 0: it is launched ordinarily; -1: the workload's measured best")
     ap.add_argument("--sim-warps", type=int, default=0, help="TzSearchCfg.sim_warps (0 = library's choice)")
     ap.add_argument("--skip-cpu", action="store_true")
     ap.add_argument("--skip-e2e", action="store_true")
@@ -288,6 +294,10 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         if world > 1:
             dist.barrier()
 
+    mode = PDL_MODE.get(wl) or (3, 1)  # (forced on for a workload whose default is ordinary launches: both bits)
+    pdl_bits = args.pdl_bits if args.pdl_bits > 0 else mode[0]
+    leaf_pdl = args.leaf_pdl if args.leaf_pdl >= 0 else mode[1]
+
     def new_eval(programmatic):
         ev = make_synthetic_evaluator(base, game, action_selector=tz.PUCTSelector(), max_nodes=N, num_iterations=S,
                                       discount=discount, temperature=1.0, programmatic=programmatic)
@@ -346,8 +356,8 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
     # ---------------- leg 1: device-resident inputs, whole move in the C-ABI (tz_search + leaf callback) ----------
     def timed_moves(programmatic, with_clocks, keep):
         """W warm-up + K timed self-play moves (one CUDA-graph replay each, per-step events, L2 flushed in between)."""
-        slib.tz_synth_set_programmatic(1 if programmatic else 0)
-        ev_ = new_eval(programmatic)
+        ev_ = new_eval(pdl_bits if programmatic else False)
+        slib.tz_synth_set_programmatic(leaf_pdl if programmatic else 0)
         sp_ = SyntheticSelfPlay(game, ev_, B, env_offset=rank * B, dirichlet=True, device=dev, stats=True)
 
         def load_inputs_(i):
@@ -538,13 +548,14 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
                               "achieved": rr_achieved, "peak": peak, "unit": "GB/s", "frac": rr_achieved / peak,
                               "avg_launch_us": rr_avg_ms * 1e3, "algorithmic_bytes_per_launch": rr_bytes,
                               "rows_before": int(rr_st[2]) / moves_r / B, "rows_kept": int(rr_st[3]) / moves_r / B}
-    slib.tz_synth_set_programmatic(1 if use_pdl else 0)
+    slib.tz_synth_set_programmatic(leaf_pdl if use_pdl else 0)
     del sp, one_move, load_inputs
 
     # ---------------- leg 3: e2e through the public Python API with host buffers -----------------------------------
     e2e = None
     if "e2e" in legs:
-        ev2 = new_eval(use_pdl)
+        ev2 = new_eval(pdl_bits if use_pdl else False)
+        slib.tz_synth_set_programmatic(leaf_pdl if use_pdl else 0)
         env = SyntheticEnv(game, B, env_offset=rank * B, device=dev)
         tree2 = ev2.init_batched(B, game.template_embedding(), device=dev)
         # the step's three random inputs live in ONE device buffer (views below), so the step costs one H2D copy
@@ -667,7 +678,8 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         "levels_per_sim": main["levels_per_sim"], "launches_per_move": main["launches_per_move"], "clocks": main["clocks"],
         "config": {"workload": desc, "envs_per_gpu": B, "envs_total": total_envs, "simulations": S, "max_nodes": N,
                    "branching_factor": F, "embedding_bytes": E, "weighted": weighted, "discount": discount,
-                   "programmatic_dependent_launch": use_pdl, "levels_per_sim": main["levels_per_sim"],
+                   "programmatic_dependent_launch": use_pdl, "programmatic_bits": pdl_bits if use_pdl else 0,
+                   "leaf_stand_in_cooperates": bool(leaf_pdl) if use_pdl else False, "levels_per_sim": main["levels_per_sim"],
                    "sim_warps": args.sim_warps,
                    "step": "one self-play move of all envs: root eval, set_root, S x (select, leaf, expand+backprop), "
                            "root action, env step, re-root" + (", replay-buffer update (tz_replay_collect, capacity "
