@@ -115,9 +115,11 @@ typedef struct TzSearchCfg {
                             Contract for bit 0: between two tz launches on the same trees the stream holds at least one
                             kernel that is launched without the programmatic attribute, or that executes
                             griddepcontrol.wait before griddepcontrol.launch_dependents (ordinary framework kernels
-                            satisfy the first form).  Pays when that kernel is short (a waiting grid is resident and takes
-                            issue slots from it): measured +12 % on configs[1] with the 2 us synthetic leaf, -7 % on the
-                            go_9x9 shape whose leaf runs 10 us (profiles/).  0: ordinary stream-ordered launches. */
+                            satisfy the first form).  Pays when that kernel is short AND cooperates (is itself launched
+                            programmatically and waits before it reads): measured on one B200 against ordinary launches
+                            (profiles/r2ak_modes.log) +16 % on configs[1] with both bits, +4 % on the 2048 shape with bit 0
+                            only, +1 % on go_9x9, -6 % on the othello shape; behind an ORDINARY leaf kernel bit 0 alone
+                            measured -1 ... -3 %.  0: ordinary stream-ordered launches (the Python API's default). */
   int32_t q_transform;   /* TZ_QT_*: the selector's q_transform (action_selection.py:70,109) */
   int32_t sim_warps;     /* warps that cooperate on ONE tree in the per-simulation kernel: 0 = library's choice (1 for narrow
                             trees, 4 for trees with more than 32 actions), 1 = one warp per tree, 2 / 4 / 8 = a CTA per tree
