@@ -20,7 +20,7 @@ def build(force: bool = False, extra_flags=(), suffix: str = "") -> None:
     LIB_DIR.mkdir(exist_ok=True)
     out = LIB_DIR / f"libtz_synth{suffix}.so"
     stamp = LIB_DIR / (out.name + ".sha256")
-    want = _digest([SRC] + sorted(HDR.glob("*.h")) + sorted(INCLUDE.glob("*.h"))) + " " + " ".join(extra_flags)
+    want = (_digest([SRC] + sorted(HDR.glob("*.h")) + sorted(INCLUDE.glob("*.h"))) + " " + " ".join(extra_flags)).strip()
     if not force and out.exists() and stamp.exists() and stamp.read_text().strip() == want:
         return
     cmd = [_nvcc(), *NVCC_FLAGS, *[f for f in extra_flags if not f.startswith("-rdc")], f"-I{INCLUDE}", f"-I{HDR}", "-shared", str(SRC), "-o", str(out)]

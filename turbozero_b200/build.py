@@ -67,7 +67,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), suffix: st
         out = LIB_DIR / out_name.replace(".so", suffix + ".so")
         src_paths = [PKG / s for s in srcs]
         stamp = LIB_DIR / (out.name + ".sha256")
-        want = _digest(src_paths + headers) + " " + " ".join(extra_flags)
+        want = (_digest(src_paths + headers) + " " + " ".join(extra_flags)).strip()  # (compared with the stamp's stripped text)
         if not force and out.exists() and stamp.exists() and stamp.read_text().strip() == want:
             continue
         obj_dir.mkdir(exist_ok=True)
