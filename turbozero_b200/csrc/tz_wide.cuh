@@ -118,6 +118,9 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
   const TzSearchCfg& cfg = P.cfg;
   constexpr int XW = W - 1;  // the warp that writes the expansion (idle in the decisions unless the path has >= W levels)
   pdl_wait();  // (no-op unless launched programmatically) everything below may read what the preceding kernel wrote
+  // (Splitting the kernel around the wait as k_sim does -- round trips 1 and 2 before it, the leaf results after -- was built
+  // and measured on one box against this form: go_9x9 36.7 -> 36.0 M with programmatic launches and 36.3 -> 35.0 M with
+  // ordinary ones, othello 26.5 -> 27.3 M programmatic but 28.0 -> 27.7 M ordinary, its best mode: profiles/r2ao_ab.log.)
   if (warp == 0) tl_min(P.tl_row, 0, lane);
   TZ_WSTAMP(0);
   const TV tv = make_view(P, b);
