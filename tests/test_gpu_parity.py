@@ -95,6 +95,14 @@ def test_programmatic_launch_vs_oracle(name, graph):
     _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=graph), name)
 
 
+@pytest.mark.parametrize("name", ["c4", "go_muzero", "g2048_pos_discount", "othello_weighted"])
+def test_programmatic_bit0_only_vs_oracle(name):
+    """TzSearchCfg.programmatic = 1: the search is launched programmatically but does not signal its dependents early (the mode
+    bench.py uses for the go_9x9 and 2048 shapes) -- same trees."""
+    s = Schedule(**CASES[name], programmatic=1)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), name)
+
+
 @pytest.mark.parametrize("name", ["c4", "othello_weighted_T05"])
 def test_programmatic_launch_python_loop_vs_oracle(name):
     s = Schedule(**CASES[name], programmatic=True)
