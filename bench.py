@@ -324,7 +324,7 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         existing gradient mean and replay-memory gather"): one sample of TRAIN_BATCH rows over the buffers of all ranks
         (replay_memory.py:137-183 / train.py:435-437: all-reduce of the valid count, all-gather of every rank's candidates,
         all-reduce of the owners' rows) and the gradient mean (train.py:393,397) of a parameter-sized buffer, enqueued eagerly
-        after the graph replay.  Returns (collect(move_fn), after_step or None, extra config)."""
+        on a second stream behind the step's buffer update (OverlappedStep below).  Returns (collect(move_fn), after_step or None, extra config)."""
         rb = tz.EpisodeReplayBuffer(capacity=REPLAY_CAPACITY)
         obs0 = get_core().to(torch.float32)
         rstate = rb.init(B, tz.BaseExperience(reward=torch.zeros((1,)), policy_weights=torch.zeros((F,)),
@@ -335,14 +335,21 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         x_player = torch.zeros((B,), dtype=torch.int32, device=dev)
         x_trunc = torch.zeros((B,), dtype=torch.uint8, device=dev)
 
-        def collect(move_fn):
+        def search_half(move_fn):
             x_obs.copy_(get_core())  # the position the search runs on (int32 -> float32 features)
             move_fn()
+
+        def buffer_half():
             x_rew.copy_(get_done().unsqueeze(1))  # stand-in reward: 1 where the episode ended
             exp = tz.BaseExperience(reward=x_rew0, policy_weights=get_pw(), policy_mask=x_mask, observation_nn=x_obs,
                                     cur_player_id=x_player)
             rb.collect_update(rstate, [exp], x_rew, get_done(), x_trunc)
 
+        def collect(move_fn):
+            search_half(move_fn)
+            buffer_half()
+
+        collect.search_half, collect.buffer_half = search_half, buffer_half
         if not with_nccl:
             return collect, None, {}
         grads = torch.zeros((GRAD_FLOATS,), dtype=torch.float32, device=dev)
@@ -351,7 +358,48 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
             rb.sample(rstate, 17, TRAIN_BATCH)
             dist.all_reduce(grads, op=dist.ReduceOp.AVG)
 
-        return collect, after, {"nccl": {"replay_sample_rows": TRAIN_BATCH, "grad_allreduce_bytes": GRAD_FLOATS * 4}}
+        return collect, after, {"nccl": {"replay_sample_rows": TRAIN_BATCH, "grad_allreduce_bytes": GRAD_FLOATS * 4,
+                                         "overlap": "the exchange legs of step i run on a second stream behind its buffer update "
+                                                    "and overlap the search of step i+1, whose buffer update waits for them"}}
+
+    class OverlappedStep:
+        """configs[4] at more than one GPU: [search of the move] [wait for the previous step's exchange legs] [replay-buffer
+        update] on the main stream, then [cross-rank sample + gradient all-reduce] on a second stream.  The sample of step i
+        sees exactly the buffer after update i (the next update waits for it), and its NCCL traffic overlaps search i+1."""
+
+        def __init__(self, search, update, after):
+            self.search, self.update, self.after = search, update, after
+            self.comm = torch.cuda.Stream()
+            self.done = None
+
+        def __call__(self):
+            main = torch.cuda.current_stream()
+            self.search()
+            if self.done is not None:
+                main.wait_event(self.done)
+            self.update()
+            ready = torch.cuda.Event()
+            ready.record(main)
+            self.comm.wait_event(ready)
+            with torch.cuda.stream(self.comm):
+                self.after()
+                self.done = torch.cuda.Event()
+                self.done.record(self.comm)
+
+        def join(self):
+            torch.cuda.current_stream().wait_stream(self.comm)
+
+    def capture(fn):
+        if args.no_graph:
+            return fn
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                fn()
+        torch.cuda.current_stream().wait_stream(side)
+        return g.replay
 
     # ---------------- leg 1: device-resident inputs, whole move in the C-ABI (tz_search + leaf callback) ----------
     def timed_moves(programmatic, with_clocks, keep):
@@ -380,22 +428,19 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
             after_step()
         torch.cuda.synchronize()
         per_move = launches() - l0
-        if args.no_graph:
-            replay = one_move
-        else:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            cg = torch.cuda.CUDAGraph()
-            with torch.cuda.stream(side):
-                with torch.cuda.graph(cg, stream=side):
-                    one_move()
-            torch.cuda.current_stream().wait_stream(side)
-            replay = cg.replay
+        overlapped = None
+        if after_step:  # two graphs, so that the buffer update alone waits for the previous step's exchange legs
+            g_search = capture(lambda: collect.search_half(sp_.move))
+            g_update = capture(collect.buffer_half)
+            overlapped = OverlappedStep(g_search, g_update, after_step)
+            step = overlapped
 
-        def step():
-            replay()
-            if after_step:
-                after_step()
+            def replay():
+                g_search()
+                g_update()
+        else:
+            replay = capture(one_move)
+            step = replay
 
         for i in range(W):
             load_inputs_(i)
@@ -413,6 +458,13 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
             evs[i][0].record()
             step()
             evs[i][1].record()
+        tail_ms = 0.0
+        if overlapped is not None:  # the last step's exchange legs have no next search to hide behind: they count in full
+            tail = torch.cuda.Event(enable_timing=True)
+            overlapped.join()
+            tail.record()
+            torch.cuda.synchronize()
+            tail_ms = evs[K - 1][1].elapsed_time(tail)
         torch.cuda.synchronize()
         ms_wall = time.perf_counter() - t_wall0
         barrier()
@@ -427,7 +479,7 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         clocks_ = sampler.stop() if sampler else None
         per_step = [a_.elapsed_time(b_) for a_, b_ in evs]
         d_st = sp_.tree.stats.sum(0).cpu().numpy().astype(np.int64) - st0
-        t_ms = torch.tensor([sum(per_step), -min(per_step), max(per_step), statistics.median(per_step)], dtype=torch.float64, device=dev)
+        t_ms = torch.tensor([sum(per_step) + tail_ms, -min(per_step), max(per_step), statistics.median(per_step)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
         res = {"ms_total": float(t_ms[0]), "ms_min": -float(t_ms[1]), "ms_max": float(t_ms[2]), "ms_median": float(t_ms[3]),
@@ -596,28 +648,20 @@ def measure_workload(cx, wl, B, K, W, *, use_pdl, legs, strong_total=None):
         user_step()
         torch.cuda.synchronize()
         api_launches = launches() - l0
-        if args.no_graph:
-            api_step = user_step
+        if e2e_after:  # (configs[4], more than one GPU) the exchange legs overlap the next step's search, as in `value`
+            api_step = OverlappedStep(capture(lambda: collect2.search_half(api_move_static)), capture(collect2.buffer_half), e2e_after)
         else:
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            cg2 = torch.cuda.CUDAGraph()
-            with torch.cuda.stream(side):
-                with torch.cuda.graph(cg2, stream=side):
-                    user_step()
-            torch.cuda.current_stream().wait_stream(side)
-            api_step = cg2.replay
+            api_step = capture(user_step)
 
         act_slots = [torch.empty((B,), dtype=torch.int32).pin_memory() for _ in range(2)]
         pw_slots = [torch.empty((B, F), dtype=torch.float32).pin_memory() for _ in range(2)]
         sink = [0.0]
 
         def enqueue(i, slot):
-            """One step: H2D of its inputs, the captured API step (+ the NCCL legs of configs[4]), D2H of its results."""
+            """One step: H2D of its inputs, the captured API step (+ the NCCL legs of configs[4], on their own stream), D2H of
+            its results.  (The timed region ends with a device-wide synchronize, so the last step's exchange legs count.)"""
             h2d(i)
             api_step()
-            if e2e_after:
-                e2e_after()
             act_slots[slot].copy_(out_box["action"], non_blocking=True)
             pw_slots[slot].copy_(out_box["pw"], non_blocking=True)
             ev = torch.cuda.Event()
