@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(32 * W, WideOcc<NC, WEIGHTED, W>::MIN_CTAS) k_
       __syncthreads();
     }
   }
-  // stage the best-table for the walk (fire-and-forget global -> shared copies; they land while the backup runs): the walk's
+  // stage the best-table for the walk (a fire-and-forget global -> shared copy; it lands while the backup runs): the walk's
   // remainder is then one shared-memory load per level instead of one dependent L2 / DRAM round trip
   int2* const sb = (P.best_rows > 0 && do_sel) ? reinterpret_cast<int2*>(wide_smem) : nullptr;
   // (one cp.async.bulk for the whole table when it is 16-byte aligned: the per-thread LDGSTS loop was 6 % of the kernel's
