@@ -948,7 +948,7 @@ int tz_reroot(const TzTree* t, const int32_t* action, const uint8_t* reset_flag,
     // Staging area: as many CTAs per SM as let every tree of the batch be resident at once (one wave over the 148 SMs, at most
     // 7) -- unless a chunk would then hold fewer than 8 destination rows (wide rows: go_9x9's are 5.4 KB): every chunk costs a
     // memory round trip, two barriers and a pass over the table list, so fewer, larger CTAs (and several waves) move more
-    // bytes per second.  Measured on the go_9x9 shape: 3 rows per chunk at 7 CTAs per SM = 2.4 TB/s (profiles/r2d).
+    // bytes per second.  Measured on the go_9x9 shape: 3 rows per chunk at 7 CTAs per SM = 2.4 TB/s (profiles/r2d_phase_reroot_go.log).
     int ctas = (t->B + 147) / 148;
     ctas = ctas < 1 ? 1 : (ctas > 7 ? 7 : ctas);
     // (the kernels' static shared memory -- descriptors, the root's edge row -- counts against the SM like the dynamic part)
