@@ -103,6 +103,17 @@ def test_programmatic_bit0_only_vs_oracle(name):
     _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), name)
 
 
+@pytest.mark.parametrize("name", ["c4", "g2048_pos_discount", "ttt_T0"])
+@pytest.mark.parametrize("programmatic", [False, True])
+def test_large_batch_several_waves_vs_oracle(name, programmatic):
+    """More trees than the SMs hold at once (6000 > 2 * 9 * 148): the per-simulation kernel runs in several waves -- same
+    trees as the oracle."""
+    c = dict(CASES[name])
+    c.update(B=6000, moves=2)
+    s = Schedule(**c, programmatic=programmatic)
+    _compare(run_c_treemajor(s), run_cuda_selfplay(s, graph=True), f"{name}, 6000 trees")
+
+
 @pytest.mark.parametrize("name", ["c4", "othello_weighted_T05"])
 def test_programmatic_launch_python_loop_vs_oracle(name):
     s = Schedule(**CASES[name], programmatic=True)
